@@ -1,0 +1,224 @@
+// k_match.cu -- Hamming matchers on 256-bit descriptors: row-band left/right match and brute force.
+//
+// (1) Row-band L/R match: replaces stereo-vo's smDescRbR stage forced at reference EST.cpp:1136 and run
+//     inside processNewImagePair (EST.cpp:112,267) with [MATCH] max_y_diff / orb_max_distance
+//     (kitti.ini:17,24) and the run-time ORB threshold (EST.cpp:284,304,311).  Conventions (stereo-vo is
+//     not vendored): candidates for left i are right j with |yl-yr| <= max_y_diff and
+//     min_disp <= xl-xr <= max_disp; best = min Hamming, lowest j on ties; accepted iff
+//     dist <= threshold; optional mutual-best (robust 1-to-1).  Output DMatch{left idx, right idx} in
+//     left order (reference KF.cpp:43-44, EST.cpp:147-151).
+// (2) Brute force: replaces cv::BFMatcher(NORM_HAMMING,false).match (reference EST.cpp:1447-1452) and
+//     the inter-frame matcher ifmDescBF (EST.cpp:1137): argmin over all train rows, lowest index on ties.
+//
+// Integer/popc work: xor + __popc on eight 32-bit words per pair, packed (dist<<16 | idx) keys so the
+// argmin with the lowest-index tie rule is a plain unsigned min (warp shuffles / atomicMin).
+// Tensor cores are deliberately not used (BASELINE.json north_star).
+#include "sfe_internal.cuh"
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1)
+{
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-band match: one CTA per stereo pair.
+// ------------------------------------------------------------------------------------------------
+#define RB_THREADS 512
+#define RB_MAX_ROWS 4096
+
+struct RowBandArgs {
+    const sfe_keypoint* kps; const uint8_t* desc; const int32_t* kp_count;
+    sfe_dmatch* matches; int32_t* match_count;
+    int kp_cap, height;
+    float max_y_diff, min_disp, max_disp;
+    int max_dist, robust;
+};
+
+__global__ void __launch_bounds__(RB_THREADS)
+rowband_kernel(const RowBandArgs a)
+{
+    extern __shared__ uint32_t dynm[];
+    // layout: row_start[height+2] | sorted[kp_cap] | best[kp_cap] | owner[kp_cap]
+    int* row_start = reinterpret_cast<int*>(dynm);
+    int* sorted = row_start + a.height + 2;
+    uint32_t* best = reinterpret_cast<uint32_t*>(sorted + a.kp_cap);
+    uint32_t* owner = best + a.kp_cap;
+    __shared__ int s_scan[RB_THREADS / 32];
+    __shared__ int s_total;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pair = blockIdx.x;
+    const int il = 2 * pair, ir = 2 * pair + 1;
+    const int nl = min(a.kp_count[il], a.kp_cap), nr = min(a.kp_count[ir], a.kp_cap);
+    const sfe_keypoint* kl = a.kps + (size_t)il * a.kp_cap;
+    const sfe_keypoint* kr = a.kps + (size_t)ir * a.kp_cap;
+    const uint4* dl = reinterpret_cast<const uint4*>(a.desc + (size_t)il * a.kp_cap * 32);
+    const uint4* dr = reinterpret_cast<const uint4*>(a.desc + (size_t)ir * a.kp_cap * 32);
+    const int H = a.height;
+
+    // ---- bucket the right keypoints by image row (counting sort) ----------------------------
+    for (int i = tid; i < H + 2; i += RB_THREADS) row_start[i] = 0;
+    for (int i = tid; i < a.kp_cap; i += RB_THREADS) owner[i] = 0xffffffffu;
+    __syncthreads();
+    for (int j = tid; j < nr; j += RB_THREADS) {
+        const int r = min(max((int)floorf(kr[j].y), 0), H - 1);
+        atomicAdd(&row_start[r + 2], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {                         // H <= 4096: a serial scan is a few microseconds
+        int acc = 0;
+        for (int r = 0; r < H; ++r) { acc += row_start[r + 2]; row_start[r + 2] = acc; }
+        // row_start[r+1] is now (after the scatter below) the begin of row r; row_start[r+2] its end
+    }
+    __syncthreads();
+    for (int j = tid; j < nr; j += RB_THREADS) {
+        const int r = min(max((int)floorf(kr[j].y), 0), H - 1);
+        const int p = atomicAdd(&row_start[r + 1], 1);
+        sorted[p] = j;
+    }
+    __syncthreads();
+    // now row r occupies sorted[row_start[r] .. row_start[r+1])
+
+    // ---- one warp per left keypoint ------------------------------------------------------------
+    for (int i = warp; i < nl; i += RB_THREADS / 32) {
+        const float xl = kl[i].x, yl = kl[i].y;
+        const uint4 q0 = __ldg(dl + 2 * i), q1 = __ldg(dl + 2 * i + 1);
+        const int rlo = min(max((int)floorf(yl - a.max_y_diff), 0), H - 1);
+        const int rhi = min(max((int)floorf(yl + a.max_y_diff), 0), H - 1);
+        const int beg = row_start[rlo], end = row_start[rhi + 1];
+        uint32_t key = 0xffffffffu;
+        for (int p = beg + lane; p < end; p += 32) {
+            const int j = sorted[p];
+            const float dy = fabsf(yl - kr[j].y), disp = xl - kr[j].x;
+            if (dy <= a.max_y_diff && disp >= a.min_disp && disp <= a.max_disp) {
+                const int d = hamming256(q0, q1, __ldg(dr + 2 * j), __ldg(dr + 2 * j + 1));
+                key = min(key, ((uint32_t)d << 16) | (uint32_t)j);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+        if (lane == 0) {
+            if (key != 0xffffffffu && (int)(key >> 16) > a.max_dist) key = 0xffffffffu;
+            best[i] = key;
+            if (a.robust && key != 0xffffffffu) atomicMin(&owner[key & 0xffffu], (key & 0xffff0000u) | (uint32_t)i);
+        }
+    }
+    __syncthreads();
+
+    // ---- ordered compaction -----------------------------------------------------------------------
+    sfe_dmatch* out = a.matches + (size_t)pair * a.kp_cap;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int base = 0; base < nl; base += RB_THREADS) {
+        const int i = base + tid;
+        bool ok = false; uint32_t key = 0xffffffffu;
+        if (i < nl) {
+            key = best[i];
+            ok = key != 0xffffffffu;
+            if (ok && a.robust) ok = (owner[key & 0xffffu] & 0xffffu) == (uint32_t)i;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_scan[warp] = __popc(bal);
+        __syncthreads();
+        int wofs = s_total;
+        for (int w = 0; w < warp; ++w) wofs += s_scan[w];
+        if (ok) {
+            sfe_dmatch m;
+            m.queryIdx = i; m.trainIdx = (int)(key & 0xffffu); m.imgIdx = 0; m.distance = (float)(key >> 16);
+            out[wofs + __popc(bal & ((1u << lane) - 1u))] = m;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = s_total; for (int w = 0; w < RB_THREADS / 32; ++w) t += s_scan[w]; s_total = t; }
+        __syncthreads();
+    }
+    if (tid == 0) a.match_count[pair] = s_total;
+}
+
+static size_t rowband_smem(const sfe_context* c)
+{
+    return sizeof(int) * ((size_t)c->cfg.height + 2 + 3 * (size_t)c->pack.kp_cap);
+}
+
+void prepare_rowband(sfe_context* c)
+{
+    cudaFuncSetAttribute(rowband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowband_smem(c));
+}
+
+void launch_match_rowband(sfe_context* c, int npairs)
+{
+    RowBandArgs a;
+    a.kps = c->d_kp; a.desc = c->d_desc; a.kp_count = c->d_kp_count;
+    a.matches = c->d_matches; a.match_count = c->d_match_count;
+    a.kp_cap = c->pack.kp_cap; a.height = c->cfg.height;
+    a.max_y_diff = c->cfg.max_y_diff; a.min_disp = c->cfg.min_disparity; a.max_disp = c->cfg.max_disparity;
+    a.max_dist = c->orb_th; a.robust = c->cfg.robust_1to1;
+    const size_t smem = rowband_smem(c);
+    rowband_kernel<<<npairs, RB_THREADS, smem, c->stream>>>(a);
+    c->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Brute force: grid (query tiles, train splits, pairs).  Each thread owns one query descriptor in
+// registers; the train split is streamed through shared memory in chunks and read as broadcasts.
+// Partial results merge with atomicMin on the packed key (d_best must be pre-set to 0xFFFFFFFF).
+// ------------------------------------------------------------------------------------------------
+#define BF_THREADS 128
+#define BF_CHUNK 128
+#define BF_SPLITS 8
+
+__global__ void bf_init_kernel(uint32_t* best, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) best[i] = 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(BF_THREADS)
+bf_kernel(const uint8_t* __restrict__ dq, const int32_t* __restrict__ q_ofs,
+          const uint8_t* __restrict__ dt, const int32_t* __restrict__ t_ofs, uint32_t* __restrict__ best)
+{
+    __shared__ uint4 ts[BF_CHUNK * 2];
+    const int pair = blockIdx.z;
+    const int qb = q_ofs[pair], nq = q_ofs[pair + 1] - qb;
+    const int tb = t_ofs[pair], nt = t_ofs[pair + 1] - tb;
+    const int q = blockIdx.x * BF_THREADS + threadIdx.x;
+    if (blockIdx.x * BF_THREADS >= nq) return;
+    // this CTA's slice of the train set
+    const int per = (nt + BF_SPLITS - 1) / BF_SPLITS;
+    const int t0 = blockIdx.y * per, t1 = min(nt, t0 + per);
+    if (t0 >= t1) return;
+    const bool active = q < nq;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    if (active) {
+        const uint4* qp = reinterpret_cast<const uint4*>(dq + (size_t)(qb + q) * 32);
+        q0 = __ldg(qp); q1 = __ldg(qp + 1);
+    }
+    const uint4* tp = reinterpret_cast<const uint4*>(dt + (size_t)tb * 32);
+    uint32_t key = 0xffffffffu;
+    for (int c0 = t0; c0 < t1; c0 += BF_CHUNK) {
+        const int n = min(BF_CHUNK, t1 - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n; i += BF_THREADS) ts[i] = __ldg(tp + 2 * (size_t)c0 + i);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const int d = hamming256(q0, q1, ts[2 * j], ts[2 * j + 1]);
+            key = min(key, ((uint32_t)d << 16) | (uint32_t)(c0 + j));
+        }
+    }
+    if (active) atomicMin(&best[qb + q], key);
+}
+
+void launch_match_bf(cudaStream_t s, const uint8_t* d_query, const int32_t* d_q_ofs, const uint8_t* d_train,
+                     const int32_t* d_t_ofs, int npairs, int max_nq, uint32_t* d_best)
+{
+    if (npairs <= 0 || max_nq <= 0) return;
+    dim3 grid((max_nq + BF_THREADS - 1) / BF_THREADS, BF_SPLITS, npairs);
+    bf_kernel<<<grid, BF_THREADS, 0, s>>>(d_query, d_q_ofs, d_train, d_t_ofs, d_best);
+}
+
+void launch_bf_init(cudaStream_t s, uint32_t* best, int n)
+{
+    if (n <= 0) return;
+    bf_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(best, n);
+}

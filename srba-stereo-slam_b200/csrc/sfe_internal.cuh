@@ -1,0 +1,169 @@
+// sfe_internal.cuh -- shared declarations of the stereo front-end CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/srba_b200.h"
+
+#define SFE_MAX_LEVELS 8
+
+// ---- tile geometry shared by host and device -------------------------------------------------
+// Pyramid: 128x16 output tile, source box fetched by one TMA load.
+#define PYR_TW 128
+#define PYR_TH 16
+#define PYR_BOX_W 160      // >= ceil(127*scale)+3, multiple of 16 (TMA inner box bytes)
+#define PYR_BOX_H 24       // >= ceil(15*scale)+3
+// FAST: 128x16 keypoint tile; scores on 130x18; pixels 136x24 -> TMA box 144x24.
+#define FAST_TW 128
+#define FAST_TH 16
+#define FAST_BOX_W 144
+#define FAST_BOX_H 24
+#define FAST_SW 132        // score tile pitch (130 used)
+#define FAST_SH 18
+// Blur: 128x16 output tile, halo 3 -> 134x22 used of a 144x24 box.
+#define BLUR_TW 128
+#define BLUR_TH 16
+#define BLUR_BOX_W 144
+#define BLUR_BOX_H 24       // shares the 144x24 maps with FAST (rows 22,23 unused)
+
+#define SEL_THREADS 512
+#define SEL_TIE_SLACK 64   // extra slots per level for Harris-response ties
+
+struct LevelGeom {
+    int w, h, pitch;            // pixels, bytes per row (multiple of 128)
+    int quota;                  // features wanted at this level
+    int sel_cap;                // quota + SEL_TIE_SLACK
+    int rx0, ry0, rx1, ry1;     // keypoint ROI [rx0,rx1) x [ry0,ry1): border filter and FAST margin
+    int ftiles_x, ftiles_y;     // FAST tiles over the ROI
+    int btiles_x, btiles_y;     // blur tiles over the level
+    int raw_cap;                // capacity of the raw corner list
+    size_t img_bytes;           // pitch * h
+    size_t lvl_ofs;             // byte offset of this level's [NI][h][pitch] block in the pyramid arena
+    size_t raw_ofs;             // entry offset of this level in one image's raw list
+    int sel_ofs;                // entry offset of this level in one image's selection list
+    float scale;                // 1.2^l (float, as OpenCV getScale)
+};
+
+// Everything the all-level kernels need, passed as one __grid_constant__ parameter.
+struct alignas(64) LevelPack {
+    CUtensorMap pyr_map[SFE_MAX_LEVELS];    // 3-D (x, y, image) u8 maps over the pyramid levels, box 144x24
+    LevelGeom g[SFE_MAX_LEVELS];
+    int nlevels;
+    int ftile_prefix[SFE_MAX_LEVELS + 1];   // blockIdx.x -> level for the FAST kernel
+    int btile_prefix[SFE_MAX_LEVELS + 1];   // blockIdx.x -> level for the blur kernel
+    size_t raw_img_stride;                  // raw entries per image
+    int sel_img_stride;                     // selection entries per image
+    int kp_cap;                             // keypoint capacity per image
+};
+
+// ---- PTX helpers: mbarrier + TMA -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled TMA load: box at (x, y, z) of the tensor map -> smem, completion on mbarrier.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- host-side context -----------------------------------------------------------------------
+enum Stage { ST_H2D = 0, ST_PYRAMID, ST_FAST, ST_SELECT, ST_BLUR, ST_DESCRIBE, ST_MATCH_LR, ST_D2H, ST_COUNT };
+
+struct sfe_context {
+    sfe_config cfg;
+    int fast_th, orb_th;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    LevelPack pack;                          // host copy (passed by value at launch)
+    std::vector<std::vector<int2>> xtab, ytab;   // host resize tables (kept for debugging)
+    int2* d_xtab[SFE_MAX_LEVELS] = {};       // per destination level: {src offset, a0 | a1<<16}
+    int2* d_ytab[SFE_MAX_LEVELS] = {};
+    CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 160x24-box maps over the same levels, source side of the pyramid kernel
+    int NI = 0;                              // images the arenas are sized for (2*max_pairs)
+    int sel_cand_cap = 0;                    // select kernel: shared candidate list capacity
+    bool select_attr_set = false;
+    uint8_t* d_pyr = nullptr;                // pyramid arena
+    uint8_t* d_blur = nullptr;               // blurred arena (same layout)
+    size_t arena_bytes = 0;
+    uint32_t* d_raw = nullptr;               // [NI][raw_img_stride]
+    int32_t* d_raw_count = nullptr;          // [NI][L]
+    uint32_t* d_sel_xy = nullptr;            // [NI][sel_img_stride]  (y<<16 | x)
+    float* d_sel_resp = nullptr;             // [NI][sel_img_stride]
+    int32_t* d_sel_count = nullptr;          // [NI][L]
+    sfe_keypoint* d_kp = nullptr;            // [NI][kp_cap]
+    uint8_t* d_desc = nullptr;               // [NI][kp_cap][32]
+    int32_t* d_kp_count = nullptr;           // [NI]
+    sfe_dmatch* d_matches = nullptr;         // [max_pairs][kp_cap]
+    int32_t* d_match_count = nullptr;        // [max_pairs]
+    int32_t* d_status = nullptr;             // [NI] device-side error flags (capacity overflow)
+    // pinned staging
+    uint8_t* h_images = nullptr; size_t h_images_bytes = 0;
+    sfe_keypoint* h_kp = nullptr; uint8_t* h_desc = nullptr; sfe_dmatch* h_matches = nullptr;
+    int32_t* h_kp_count = nullptr; int32_t* h_match_count = nullptr; int32_t* h_status = nullptr;
+    sfe_pair_counts* h_counts = nullptr;
+    int last_npairs = 0; bool have_results = false; bool downloaded = false;
+    // graph cache, one per batch size
+    std::vector<cudaGraphExec_t> graphs;
+    // timing
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev_stage[ST_COUNT + 1] = {};
+    int graph_kernels = 0;                   // kernels per graph replay
+    int64_t launches = 0;
+    // scratch for sfe_match_bf host entry
+    uint8_t* d_bf_q = nullptr; uint8_t* d_bf_t = nullptr; uint32_t* d_bf_best = nullptr; int32_t* d_bf_ofs = nullptr;
+    int bf_cap_q = 0, bf_cap_t = 0;
+};
+
+#define SFE_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+            return SFE_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+// kernel launchers (defined in the per-stage .cu files)
+void launch_pyramid_level(sfe_context* c, int level, int nimg);
+void launch_fast(sfe_context* c, int nimg);
+void launch_select(sfe_context* c, int nimg);
+void prepare_select(sfe_context* c);
+void prepare_rowband(sfe_context* c);
+void launch_blur(sfe_context* c, int nimg);
+void launch_describe(sfe_context* c, int nimg);
+void launch_match_rowband(sfe_context* c, int npairs);
+void launch_match_bf(cudaStream_t s, const uint8_t* d_query, const int32_t* d_q_ofs, const uint8_t* d_train,
+                     const int32_t* d_t_ofs, int npairs, int max_nq, uint32_t* d_best);

@@ -1,0 +1,228 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact pyramid pixels, FAST keypoint sets, match indices and BoW word
+ids; descriptors <= 0.1 % bit disagreement (we assert 0), orientation within 1e-3 rad (we assert bit-equal
+degrees).  Field lists follow the reference's equality helpers (srba-stereo-slam_utils.cpp:49-59,75).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from srba_stereo_slam_b200 import frontend
+    from oracle import oracle as orc
+    return frontend, orc
+
+
+def _roi_filter(xs, ys, sc, w, h, e=31):
+    m = (xs >= e) & (xs < w - e) & (ys >= e) & (ys < h - e)
+    return set(zip(xs[m].tolist(), ys[m].tolist(), sc[m].tolist()))
+
+
+def _assert_keypoints_equal(a, b):
+    assert len(a) == len(b)
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(a[f], b[f]), f
+
+
+@pytest.mark.parametrize("blur_mode", [0, 1])
+def test_config_b_full_pipeline(mods, scene_frames, blur_mode):
+    """1241x376, 1000 ORB, 8 levels, L/R row-band match (BASELINE.json configs[1]) on 2 stereo pairs."""
+    frontend, orc = mods
+    frames = scene_frames(2)
+    fe = frontend.StereoFrontEnd(max_pairs=2, blur_mode=blur_mode)
+    try:
+        assert fe.process_batch_host(frames) == 2
+        for p in range(2):
+            kl, kr, dl, dr, m = fe.get_values(p)
+            sides = []
+            for s, (gk, gd) in enumerate(((kl, dl), (kr, dr))):
+                img = frames[p, s]
+                ok, od, ex = orc.orb_extract(img, nfeatures=1000, nlevels=8, fast_threshold=20, want_levels=True, blur_mode=blur_mode)
+                for l in range(8):
+                    assert np.array_equal(fe.get_level(2 * p + s, l), ex["pyramid"][l]), ("pyramid", p, s, l)
+                    assert np.array_equal(fe.get_level(2 * p + s, l, blurred=True), ex["blurred"][l]), ("blur", p, s, l)
+                    xs, ys, sc = orc.fast9_nms(ex["pyramid"][l], 20)
+                    gx, gy, gs = fe.get_raw_corners(2 * p + s, l)
+                    h, w = ex["pyramid"][l].shape
+                    assert set(zip(gx.tolist(), gy.tolist(), gs.tolist())) == _roi_filter(xs, ys, sc, w, h), ("fast", p, s, l)
+                _assert_keypoints_equal(gk, ok)
+                assert np.array_equal(gd, od)
+                assert len(gk) >= 900
+                sides.append((ok, od))
+            om = orc.match_rowband(sides[0][0], sides[0][1], sides[1][0], sides[1][1], max_y_diff=2.0, max_dist=60)
+            assert len(om) > 100
+            for f in ("queryIdx", "trainIdx", "imgIdx", "distance"):
+                assert np.array_equal(m[f], om[f]), f
+    finally:
+        fe.close()
+
+
+def test_config_a_shipped_ini(mods, scene_frames):
+    """kitti.ini as shipped: 1226x370 camera, 500 features, n_levels = 1, FAST 20, ORB 60."""
+    frontend, orc = mods
+    frames = scene_frames(1, width=1226, height=370, seed=1)
+    fe = frontend.StereoFrontEnd(width=1226, height=370, nlevels=1, nfeatures=500, max_pairs=1)
+    try:
+        fe.process_stereo(frames[0, 0], frames[0, 1])
+        kl, kr, dl, dr, m = fe.get_values(0)
+        ol, odl, _ = orc.orb_extract(frames[0, 0], nfeatures=500, nlevels=1)
+        orr, odr, _ = orc.orb_extract(frames[0, 1], nfeatures=500, nlevels=1)
+        _assert_keypoints_equal(kl, ol); _assert_keypoints_equal(kr, orr)
+        assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+        om = orc.match_rowband(ol, odl, orr, odr)
+        assert np.array_equal(m["trainIdx"], om["trainIdx"]) and np.array_equal(m["queryIdx"], om["queryIdx"])
+    finally:
+        fe.close()
+
+
+def test_golden_cv2_orb_single_level(mods, golden):
+    """The CUDA path against the committed cv2.ORB(nlevels=1) outputs directly (blur_mode 1)."""
+    frontend, _ = mods
+    g = golden("orb_nl1.npz")
+    for i in range(int(g["n"])):
+        img = g["img_%d" % i]
+        h, w = img.shape
+        fe = frontend.StereoFrontEnd(width=w, height=h, nlevels=1, nfeatures=int(g["nf_%d" % i]),
+                                     fast_threshold=int(g["th_%d" % i]), blur_mode=1, max_pairs=1)
+        try:
+            fe.process_stereo(img, img)
+            kl, kr, dl, dr, m = fe.get_values(0)
+        finally:
+            fe.close()
+        ref, rdesc = g["kp_%d" % i], g["desc_%d" % i]
+        o = np.lexsort((ref[:, 0], ref[:, 1]))
+        ref, rdesc = ref[o], rdesc[o]
+        assert len(kl) == len(ref)
+        for j, f in enumerate(("x", "y", "size", "angle", "response")):
+            assert np.array_equal(kl[f], ref[:, j].astype(np.float32)), f
+        assert np.array_equal(dl, rdesc) and np.array_equal(dr, rdesc)
+        # identical images: every left keypoint matches itself at distance 0 (disparity 0 is allowed)
+        assert np.array_equal(m["queryIdx"], m["trainIdx"]) and np.all(m["distance"] == 0) and len(m) == len(kl)
+
+
+def test_runtime_thresholds_and_repeat(mods, scene_frames):
+    """setFASTThreshold / setORBThreshold + request.repeat (EST.cpp:263-315)."""
+    frontend, orc = mods
+    frames = scene_frames(1)
+    fe = frontend.StereoFrontEnd(max_pairs=1, nfeatures=600)
+    try:
+        fe.process_stereo(frames[0, 0], frames[0, 1])
+        k20 = fe.get_values(0)[0]
+        fe.set_fast_threshold(9); fe.set_orb_threshold(35)
+        assert fe.get_fast_threshold() == 9 and fe.get_orb_threshold() == 35
+        fe.process_stereo(None, None, repeat=True)
+        kl, kr, dl, dr, m = fe.get_values(0)
+        ol, odl, _ = orc.orb_extract(frames[0, 0], nfeatures=600, fast_threshold=9)
+        orr, odr, _ = orc.orb_extract(frames[0, 1], nfeatures=600, fast_threshold=9)
+        _assert_keypoints_equal(kl, ol); _assert_keypoints_equal(kr, orr)
+        om = orc.match_rowband(ol, odl, orr, odr, max_dist=35)
+        assert np.array_equal(m["trainIdx"], om["trainIdx"]) and np.array_equal(m["distance"], om["distance"])
+        assert np.all(m["distance"] <= 35)
+        assert not (len(k20) == len(kl) and np.array_equal(k20["x"], kl["x"]))
+    finally:
+        fe.close()
+
+
+def test_edge_cases(mods):
+    frontend, orc = mods
+    fe = frontend.StereoFrontEnd(width=320, height=240, nlevels=4, nfeatures=200, max_pairs=1, robust_1to1=1)
+    try:
+        flat = np.full((240, 320), 128, np.uint8)
+        fe.process_stereo(flat, flat)                                   # no corners at all
+        kl, kr, dl, dr, m = fe.get_values(0)
+        assert len(kl) == len(kr) == len(m) == 0
+        rng = np.random.default_rng(5)
+        img = (rng.random((240, 320)) * 255).astype(np.uint8)           # white noise: corners everywhere, many score ties
+        fe.process_stereo(img, img[:, ::-1].copy())
+        kl, kr, dl, dr, m = fe.get_values(0)
+        ol, odl, _ = orc.orb_extract(img, nfeatures=200, nlevels=4)
+        orr, odr, _ = orc.orb_extract(img[:, ::-1].copy(), nfeatures=200, nlevels=4)
+        _assert_keypoints_equal(kl, ol); _assert_keypoints_equal(kr, orr)
+        assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+        om = orc.match_rowband(ol, odl, orr, odr, robust_1to1=True)
+        assert np.array_equal(m["queryIdx"], om["queryIdx"]) and np.array_equal(m["trainIdx"], om["trainIdx"])
+    finally:
+        fe.close()
+    with pytest.raises(frontend.SfeError):
+        frontend.StereoFrontEnd(width=32, height=32)
+    with pytest.raises(frontend.SfeError):
+        frontend.StereoFrontEnd(nlevels=9)
+
+
+def test_match_bf(mods, golden):
+    """cv::BFMatcher(NORM_HAMMING,false).match (EST.cpp:1447-1452): golden vectors + oracle at 1000x1000 and ragged sizes."""
+    frontend, orc = mods
+    fe = frontend.StereoFrontEnd(width=320, height=240, nlevels=1, nfeatures=100, max_pairs=1)
+    try:
+        g = golden("bf.npz")
+        m = fe.match_bf(g["Q"], g["T"])
+        ref = g["m"]
+        assert np.array_equal(m["queryIdx"], ref[:, 0]) and np.array_equal(m["trainIdx"], ref[:, 1])
+        assert np.array_equal(m["distance"], ref[:, 3].astype(np.float32)) and np.all(m["imgIdx"] == 0)
+        rng = np.random.default_rng(11)
+        for nq, nt in ((1000, 1000), (1, 1), (37, 4000), (4000, 13), (129, 129), (500, 0), (0, 500)):
+            Q = rng.integers(0, 256, (nq, 32), dtype=np.uint8); T = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+            if nt > 8 and nq > 8:
+                T[nt // 2] = Q[nq // 3]; T[nt - 1] = Q[nq // 3]; T[0] = T[min(5, nt - 1)]    # planted ties
+            m = fe.match_bf(Q, T); om = orc.match_bf(Q, T)
+            assert len(m) == len(om)
+            for f in ("queryIdx", "trainIdx", "imgIdx", "distance"):
+                assert np.array_equal(m[f], om[f]), (nq, nt, f)
+    finally:
+        fe.close()
+
+
+def test_bow_transform_vector_query(mods, voc, scene_frames):
+    """CBoWManager (CBoWManager.h:44-111): word ids bit-exact, FP64 BoW vectors and scores bit-identical."""
+    frontend, orc = mods
+    fe = frontend.StereoFrontEnd(max_pairs=1)
+    db = frontend.BowDatabase(fe, voc)
+    try:
+        rng = np.random.default_rng(7)
+        frames = scene_frames(2)
+        sets = []
+        for p in range(2):
+            k, d, _ = orc.orb_extract(frames[p, 0]); sets.append(d)
+        sets.append(rng.integers(0, 256, (1000, 32), dtype=np.uint8))
+        sets.append(rng.integers(0, 256, (3, 32), dtype=np.uint8))
+        sets.append(np.repeat(sets[0][:5], 50, axis=0))                # repeated words -> accumulation order
+        odb = []
+        for i, d in enumerate(sets):
+            w, wt = db.transform(d); ow, owt = orc.bow_transform(voc, d)
+            assert np.array_equal(w, ow) and np.array_equal(wt, owt), i
+            vw, vv = db.vector(d); ovw, ovv = orc.bow_vector(voc, ow, owt)
+            assert np.array_equal(vw, ovw) and np.array_equal(vv, ovv), i
+            assert db.add(d) == i
+            odb.append((ovw, ovv))
+        assert db.size() == len(sets)
+        queries = sets + [np.concatenate([sets[0][:400], sets[1][:300], sets[2][:100]])]
+        for q in queries:
+            res = db.query(q, 4); ores = orc.bow_query(voc, odb, q, 4)
+            assert [r[0] for r in res] == [r[0] for r in ores]
+            assert [r[1] for r in res] == [r[1] for r in ores]
+        assert db.query(sets[0], 4)[0] == (0, 1.0)
+    finally:
+        db.close(); fe.close()
+
+
+def test_capacity_and_larger_config(mods, scene_frames):
+    """1920x1080, 4000 ORB, 8 levels (BASELINE.json configs[4]), one pair: keypoint sets + descriptors + matches."""
+    frontend, orc = mods
+    from srba_stereo_slam_b200 import synth
+    frames = synth.CorridorScene(seed=2, width=1920, height=1080).sequence(1)
+    fe = frontend.StereoFrontEnd(width=1920, height=1080, nfeatures=4000, max_pairs=1)
+    try:
+        fe.process_batch_host(frames)
+        kl, kr, dl, dr, m = fe.get_values(0)
+        ol, odl, _ = orc.orb_extract(frames[0, 0], nfeatures=4000)
+        orr, odr, _ = orc.orb_extract(frames[0, 1], nfeatures=4000)
+        _assert_keypoints_equal(kl, ol); _assert_keypoints_equal(kr, orr)
+        assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+        om = orc.match_rowband(ol, odl, orr, odr)
+        assert np.array_equal(m["trainIdx"], om["trainIdx"]) and np.array_equal(m["queryIdx"], om["queryIdx"])
+    finally:
+        fe.close()
