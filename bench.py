@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s of the B200-native front-end (BASELINE.json metric) + roofline + CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl ours|reference] [--workload b|full]
+
+A "step" is one pass of the hot path over one batch of B synthetic stereo pairs.  At N=1 the workload is
+BASELINE.json configs[1]: KITTI-shaped 1241x376 stereo, 1000 ORB/img, 8-level pyramid, L/R row-band matching.
+  value      whole-job stereo frames/s with the batch already resident in HBM (device-timed, CUDA events on the
+             library's stream, max over ranks).
+  e2e        the same metric through the host-buffer C-ABI call: every step copies its images from pinned host
+             memory to the device, runs all kernels and copies keypoints/descriptors/matches back.
+  roofline   dominant kernel's achieved algorithmic GB/s (SURVEY.md 8(d) bytes) / MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (port of the reference's OpenCV-2.4/stereo-vo path) on a bounded sample.
+N>1 (torchrun, one rank per GPU): frames shard across ranks with no data-path collective ("scaling": "weak").
+`--impl reference` times the CPU oracle port on all host cores (the reference itself cannot be built here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+W, H, NFEAT, NLEVELS = 1241, 376, 1000, 8
+METRIC = "stereo frames/sec (1241x376, 1000 ORB, 8 levels, extract L+R + L/R row-band match)"
+
+
+def level_pixels(w=W, h=H, nlevels=NLEVELS):
+    # same arithmetic as cv::ORB (float 1.2^l, cvRound) -- sizes for the algorithmic-bytes table
+    px = []
+    for l in range(nlevels):
+        s = np.float32(1.0) / np.float32(np.float64(np.float32(1.2)) ** l)
+        px.append(int(np.rint(np.float32(w) * s)) * int(np.rint(np.float32(h) * s)))
+    return px
+
+
+def algorithmic_bytes_per_image(nkp=NFEAT):
+    """SURVEY.md 8(d): unfused-minimum HBM bytes per image for each stage."""
+    px = level_pixels()
+    P, A0 = sum(px), px[0]
+    return {"pyramid": A0 + (P - A0), "fast_nms": P, "blur": 2 * P, "orient_brief": nkp * (37 * 37 + 60),
+            "select_harris": 0, "match_rowband": 0, "P": P, "A0": A0}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []; self.p = None; self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_throughput(frames, threads, seconds_budget=20.0):
+    """Oracle (CPU port of the reference path) on a bounded sample: extract L+R + row-band match per pair."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    orc.lib()
+
+    def one(pair):
+        kl, dl, _ = orc.orb_extract(pair[0], nfeatures=NFEAT, nlevels=NLEVELS, fast_threshold=20)
+        kr, dr, _ = orc.orb_extract(pair[1], nfeatures=NFEAT, nlevels=NLEVELS, fast_threshold=20)
+        return len(orc.match_rowband(kl, dl, kr, dr, max_y_diff=2.0, max_dist=60))
+    t0 = time.perf_counter(); one(frames[0]); t1 = time.perf_counter() - t0       # calibrate
+    n = int(max(threads, min(len(frames) * 64, threads * max(1, int(seconds_budget / max(t1, 1e-3))))))
+    work = [frames[i % len(frames)] for i in range(n)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:     # ctypes releases the GIL: real parallelism
+        list(ex.map(one, work))
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from srba_stereo_slam_b200 import synth
+    cores = os.cpu_count() or 1
+    frames = synth.stereo_batch(4, W, H, seed=0, unique=4)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_port_throughput(frames, cores, seconds_budget=2.0)
+    n_tot = 0; t_tot = 0.0
+    for _ in range(args.steps):
+        v, n, dt = cpu_port_throughput(frames, cores, seconds_budget=max(4.0, 60.0 / max(args.steps, 1)))
+        n_tot += n; t_tot += dt
+    value = n_tot / t_tot
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "stereo frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1241x376 stereo, 1000 ORB, 8 levels, L/R row-band match", "pairs_per_step": n_tot // max(args.steps, 1)},
+            "cpu_baseline": {"value": value, "unit": "stereo frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d stereo pairs over %d steps on %d host threads (oracle/frontend_oracle.c; the reference's OpenCV-2.4/stereo-vo path cannot be built here)" % (n_tot, args.steps, cores)},
+            "e2e": {"value": value, "unit": "stereo frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from srba_stereo_slam_b200 import frontend, synth
+
+    B = args.pairs
+    frames = synth.stereo_batch(B, W, H, seed=rank, unique=8)        # [B,2,H,W] uint8, 8 rendered frames tiled
+    fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=NLEVELS, nfeatures=NFEAT, max_pairs=B, device=local)
+    stage = fe.host_staging()
+    stage[:2 * B] = frames.reshape(-1, H, W)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local) if torch.cuda.is_available() else None
+        fe.synchronize()
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------------
+    fe.upload(frames)
+    for _ in range(args.warmup):
+        fe.process_device(B)
+    fe.synchronize()
+    kl, kr, dl, dr, m = fe.get_values(0)
+    feats = (len(kl), len(kr), len(m))
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    l0 = fe.kernel_launches()
+    fe.timer_start()
+    for _ in range(args.steps):
+        fe.process_device(B)
+    ms = fe.timer_stop()
+    barrier()
+    launches = fe.kernel_launches() - l0
+    clk = clocks.stop()
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H every step) -------------------------
+    for _ in range(2):
+        fe.process_staged(B); fe.download_batch()
+    barrier()
+    t0 = time.perf_counter()
+    fe.timer_start()
+    for _ in range(args.steps):
+        fe.process_staged(B)
+        fe.download_batch()
+    ms_e2e = fe.timer_stop()
+    barrier()
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.item())
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    cap = fe.kp_cap
+    h2d = 2 * B * W * H
+    d2h = 2 * B * cap * (28 + 32) + B * cap * 16 + 2 * B * 4 * 2 + B * 4
+
+    # ---- per-kernel times, live (CUDA events around each stage, direct launches) --------------------------------
+    fe.set_profiling(True)
+    acc = {}
+    reps = max(3, min(args.steps, 10))
+    for i in range(reps + 1):
+        fe.process_device(B); fe.synchronize()
+        st = fe.stage_times()
+        if i == 0:
+            continue
+        for k, (t_ms, n) in st.items():
+            acc.setdefault(k, [0.0, n]); acc[k][0] += t_ms
+    fe.set_profiling(False)
+    stages = {k: {"ms": v[0] / reps, "launches": v[1]} for k, v in acc.items() if k not in ("h2d", "d2h")}
+    ab = algorithmic_bytes_per_image(feats[0])
+    nimg = 2 * B
+    for k in stages:
+        stages[k]["algorithmic_bytes"] = ab.get(k, 0) * nimg
+        stages[k]["GBps"] = stages[k]["algorithmic_bytes"] / (stages[k]["ms"] * 1e-3) / 1e9 if stages[k]["ms"] > 0 else 0.0
+    hbm_stages = [k for k in ("pyramid", "fast_nms", "blur", "orient_brief") if k in stages]
+    dom = max(hbm_stages, key=lambda k: stages[k]["ms"])
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"]); peak_src = "measured"
+    except Exception:
+        pass
+    per_launch_bytes = stages[dom]["algorithmic_bytes"] / max(stages[dom]["launches"], 1)
+    per_launch_ms = stages[dom]["ms"] / max(stages[dom]["launches"], 1)
+    achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                "stages": stages}
+
+    # ---- CPU baseline (rank 0, N=1 only, bounded sample) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, n, dt = cpu_port_throughput(frames[:4], 1, seconds_budget=12.0)
+        cpu = {"value": v, "unit": "stereo frames/s", "cores": 1, "kind": "port",
+               "sample": "%d stereo pairs of the same workload in %.1f s, single thread (oracle/frontend_oracle.c)" % (n, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "stereo frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": "configs[1]: 1241x376 stereo, 1000 ORB, 8 levels, L/R row-band match", "pairs_per_step_per_gpu": B,
+                           "keypoints_left_right_matches_pair0": feats,
+                           "l2": "per-step working set %.0f MB (pyramid + blurred arenas of %d images) exceeds the 126 MB L2" % (2 * nimg * 1.55, nimg),
+                           "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world},
+                "e2e": {"value": e2e, "unit": "stereo frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    fe.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,12 +36,13 @@ blur_kernel(const __grid_constant__ LevelPack P, uint8_t* __restrict__ blur)
     const int x0 = (t % g.btiles_x) * BLUR_TW, y0 = (t / g.btiles_x) * BLUR_TH;
     const int img = blockIdx.y;
     const int w = g.w, h = g.h;
+    const int bx0 = (x0 - 3) & ~15;               // TMA: box start must be 16-byte aligned in x
 
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar, BLUR_BOX_H * BLUR_BOX_W);
-        tma_load_3d(tile, &P.pyr_map[level], x0 - 3, y0 - 3, img, &bar);
+        tma_load_3d(tile, &P.pyr_map[level], bx0, y0 - 3, img, &bar);
     }
     mbar_wait(&bar, 0);
 
@@ -50,13 +51,14 @@ blur_kernel(const __grid_constant__ LevelPack P, uint8_t* __restrict__ blur)
         const int r = i >> 7, x = i & 127;
         int iy = y0 - 3 + r;                               // image row of this tile row (reflect-101)
         iy = iy < 0 ? -iy : (iy >= h ? 2 * h - 2 - iy : iy);
-        const uint8_t* row = tile + (iy - (y0 - 3)) * BLUR_BOX_W;
+        const int tr = min(max(iy - (y0 - 3), 0), BLUR_BOX_H - 1);   // only rows feeding y >= h can clamp
+        const uint8_t* row = tile + tr * BLUR_BOX_W;
         int acc_i = 0; float acc_f = 0.f;
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             int ix = x0 + x - 3 + k;
             ix = ix < 0 ? -ix : (ix >= w ? 2 * w - 2 - ix : ix);
-            int tx = ix - (x0 - 3);
+            int tx = ix - bx0;
             tx = min(max(tx, 0), BLUR_BOX_W - 1);          // only padding columns (x >= w) can clamp
             const int v = row[tx];
             if (MODE == SFE_BLUR_CV24_FIXED) acc_i += c_taps_i[k] * v;

@@ -221,7 +221,8 @@ extern "C" int sfe_bow_create(sfe_context* ctx, int nnodes, int nwords, const in
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_top_n, sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_vn, sizeof(int32_t));
     if (e != cudaSuccess) { ctx->err = std::string("sfe_bow_create: ") + cudaGetErrorString(e); sfe_bow_destroy(b); return SFE_ERR_CUDA; }
-    cudaFuncSetAttribute(bow_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 4);
+    cudaFuncSetAttribute(bow_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
+    cudaGetLastError();
     *out = b;
     return SFE_OK;
 }
@@ -265,7 +266,7 @@ extern "C" int sfe_bow_transform_device(sfe_bow* b, const uint8_t* d_desc, int n
 // host descriptors -> device words/weights (+ BoW vector in d_vw/d_vv/d_vn when want_vector)
 static int bow_run(sfe_bow* b, const uint8_t* desc, int n, bool want_vector)
 {
-    if (n > 65535) { b->ctx->err = "more than 65535 descriptors per keyframe"; return SFE_ERR_INVALID; }
+    if (n > 32768) { b->ctx->err = "more than 32768 descriptors per keyframe"; return SFE_ERR_INVALID; }
     int r = bow_reserve(b, n); if (r) return r;
     cudaStream_t s = b->ctx->stream;
     BOW_CUDA(b, cudaMemcpyAsync(b->d_in, desc, (size_t)n * 32, cudaMemcpyHostToDevice, s));

@@ -48,18 +48,20 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
     const int tx0 = g.rx0 + (t % g.ftiles_x) * FAST_TW;
     const int ty0 = g.ry0 + (t / g.ftiles_x) * FAST_TH;
     const int img = blockIdx.y;
+    const int bx0 = (tx0 - 4) & ~15;              // TMA: box start must be 16-byte aligned in x
+    const int xoff = tx0 - 4 - bx0;               // tile column of pixel tx0-4
 
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); ncand = 0; }
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar, FAST_BOX_H * FAST_BOX_W);
-        tma_load_3d(tile, &P.pyr_map[level], tx0 - 4, ty0 - 4, img, &bar);
+        tma_load_3d(tile, &P.pyr_map[level], bx0, ty0 - 4, img, &bar);
     }
     for (int i = tid; i < FAST_SH * FAST_SW / 4; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0u;
     mbar_wait(&bar, 0);
 
     // ---- A: quick reject on the 130x18 score positions ------------------------------------
-    // score position (sx, sy) <-> pixel (tx0-1+sx, ty0-1+sy) <-> tile byte (sx+3, sy+3)
+    // score position (sx, sy) <-> pixel (tx0-1+sx, ty0-1+sy) <-> tile byte (sx+3+xoff, sy+3)
     const int w = g.w, h = g.h;
     for (int base = 0; base < FAST_SH * 130; base += 256) {
         const int pos = base + tid;
@@ -68,7 +70,7 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
             const int sy = pos / 130, sx = pos - sy * 130;
             const int px = tx0 - 1 + sx, py = ty0 - 1 + sy;
             if (px >= 3 && px < w - 3 && py >= 3 && py < h - 3) {
-                const uint8_t* c = tile + (sy + 3) * FAST_BOX_W + sx + 3;
+                const uint8_t* c = tile + (sy + 3) * FAST_BOX_W + sx + 3 + xoff;
                 const int v = c[0];
                 const int lo = v - th, hi = v + th;
                 const int p0 = c[3 * FAST_BOX_W], p8 = c[-3 * FAST_BOX_W], p4 = c[3], p12 = c[-3];
@@ -93,7 +95,7 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
     for (int i = tid; i < nc; i += 256) {
         const int pos = cand[i];
         const int sy = pos / 130, sx = pos - sy * 130;
-        const uint8_t* c = tile + (sy + 3) * FAST_BOX_W + sx + 3;
+        const uint8_t* c = tile + (sy + 3) * FAST_BOX_W + sx + 3 + xoff;
         const int v = c[0];
         int d[16];
         d[0] = c[3 * FAST_BOX_W] - v;       d[1] = c[3 * FAST_BOX_W + 1] - v;

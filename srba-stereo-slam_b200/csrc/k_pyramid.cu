@@ -6,7 +6,7 @@
 // int32, vertical pass (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.  The coefficient tables
 // are computed on the host exactly as OpenCV does (double/float) so the kernel is pure integer.
 //
-// One CTA = one 128x16 destination tile of one image.  Its source footprint (<= 160x24 u8) is
+// One CTA = one 128x16 destination tile of one image.  Its source footprint (<= 176x24 u8 incl. alignment slack) is
 // fetched with a single 3-D TMA load (out-of-bounds rows/columns arrive as zeros and are never
 // weighted).  HBM-bound by design: per destination pixel ~1.44 source bytes read + 1 byte written.
 #include "sfe_internal.cuh"
@@ -25,12 +25,13 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PYR_TW, y0 = blockIdx.y * PYR_TH, img = blockIdx.z;
     const int sx0 = a.xtab[x0].x;
+    const int bx0 = sx0 & ~15;                    // TMA: box start must be 16-byte aligned in x
     const int sy0 = max(a.ytab[y0].x, 0);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar, PYR_BOX_H * PYR_BOX_W);
-        tma_load_3d(tile, &src_map, sx0, sy0, img, &bar);
+        tma_load_3d(tile, &src_map, bx0, sy0, img, &bar);
     }
     // while the tile is in flight: this thread's 8 destination columns and its row
     const int tx = (tid & 15) * 8, ty = tid >> 4;
@@ -49,7 +50,7 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     uint32_t out[2] = { 0u, 0u };
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int sx = xt[i].x - sx0;
+        const int sx = xt[i].x - bx0;
         const int a0 = (short)(xt[i].y & 0xffff), a1 = (short)(xt[i].y >> 16);
         const int h0 = S0[sx] * a0 + S0[sx + 1] * a1;
         const int h1 = S1[sx] * a0 + S1[sx + 1] * a1;

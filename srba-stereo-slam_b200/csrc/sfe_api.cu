@@ -183,7 +183,7 @@ static int create_impl(sfe_context* c)
         // footprint check against the fixed TMA box
         for (int x0 = 0; x0 < P.g[l].w; x0 += PYR_TW) {
             const int x1 = std::min(x0 + PYR_TW, P.g[l].w) - 1;
-            if (c->xtab[l][x1].x + 2 - c->xtab[l][x0].x > PYR_BOX_W) { c->err = "pyramid tile footprint exceeds TMA box (x)"; return SFE_ERR_INVALID; }
+            if (c->xtab[l][x1].x + 2 - (c->xtab[l][x0].x & ~15) > PYR_BOX_W) { c->err = "pyramid tile footprint exceeds TMA box (x)"; return SFE_ERR_INVALID; }
         }
         for (int y0 = 0; y0 < P.g[l].h; y0 += PYR_TH) {
             const int y1 = std::min(y0 + PYR_TH, P.g[l].h) - 1;
@@ -204,7 +204,7 @@ static int create_impl(sfe_context* c)
         if (!fn || qres != cudaDriverEntryPointSuccess) { c->err = "cuTensorMapEncodeTiled not available"; return SFE_ERR_CUDA; }
         enc = (PFN_encodeTiled)fn;
     }
-    // The box shape is baked into a map: pyr_map[] (144x24) serves FAST and blur, pyrsrc_map[] (160x24)
+    // The box shape is baked into a map: pyr_map[] (160x24) serves FAST and blur, pyrsrc_map[] (176x24)
     // the source side of the pyramid kernel.
     for (int l = 0; l < L; ++l) {
         const LevelGeom& g = P.g[l];

@@ -14,20 +14,21 @@
 // Pyramid: 128x16 output tile, source box fetched by one TMA load.
 #define PYR_TW 128
 #define PYR_TH 16
-#define PYR_BOX_W 160      // >= ceil(127*scale)+3, multiple of 16 (TMA inner box bytes)
+#define PYR_BOX_W 176      // >= ceil(127*scale)+3 + 15 (16-byte aligned box start), multiple of 16
 #define PYR_BOX_H 24       // >= ceil(15*scale)+3
-// FAST: 128x16 keypoint tile; scores on 130x18; pixels 136x24 -> TMA box 144x24.
+// FAST: 128x16 keypoint tile; scores on 130x18; pixels 136x24 (+15 alignment slack) -> TMA box 160x24.
+// TMA needs the box start 16-byte aligned in x: kernels round the start down and keep the offset.
 #define FAST_TW 128
 #define FAST_TH 16
-#define FAST_BOX_W 144
+#define FAST_BOX_W 160
 #define FAST_BOX_H 24
 #define FAST_SW 132        // score tile pitch (130 used)
 #define FAST_SH 18
-// Blur: 128x16 output tile, halo 3 -> 134x22 used of a 144x24 box.
+// Blur: 128x16 output tile, halo 3 -> 134x22 used of a 160x24 box.
 #define BLUR_TW 128
 #define BLUR_TH 16
-#define BLUR_BOX_W 144
-#define BLUR_BOX_H 24       // shares the 144x24 maps with FAST (rows 22,23 unused)
+#define BLUR_BOX_W 160
+#define BLUR_BOX_H 24       // shares the 160x24 maps with FAST (rows 22,23 unused)
 
 #define SEL_THREADS 512
 #define SEL_TIE_SLACK 64   // extra slots per level for Harris-response ties
@@ -49,7 +50,7 @@ struct LevelGeom {
 
 // Everything the all-level kernels need, passed as one __grid_constant__ parameter.
 struct alignas(64) LevelPack {
-    CUtensorMap pyr_map[SFE_MAX_LEVELS];    // 3-D (x, y, image) u8 maps over the pyramid levels, box 144x24
+    CUtensorMap pyr_map[SFE_MAX_LEVELS];    // 3-D (x, y, image) u8 maps over the pyramid levels, box 160x24
     LevelGeom g[SFE_MAX_LEVELS];
     int nlevels;
     int ftile_prefix[SFE_MAX_LEVELS + 1];   // blockIdx.x -> level for the FAST kernel
@@ -110,7 +111,7 @@ struct sfe_context {
     std::vector<std::vector<int2>> xtab, ytab;   // host resize tables (kept for debugging)
     int2* d_xtab[SFE_MAX_LEVELS] = {};       // per destination level: {src offset, a0 | a1<<16}
     int2* d_ytab[SFE_MAX_LEVELS] = {};
-    CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 160x24-box maps over the same levels, source side of the pyramid kernel
+    CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 176x24-box maps over the same levels, source side of the pyramid kernel
     int NI = 0;                              // images the arenas are sized for (2*max_pairs)
     int sel_cand_cap = 0;                    // select kernel: shared candidate list capacity
     bool select_attr_set = false;

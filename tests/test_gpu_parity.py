@@ -112,17 +112,17 @@ def test_runtime_thresholds_and_repeat(mods, scene_frames):
     try:
         fe.process_stereo(frames[0, 0], frames[0, 1])
         k20 = fe.get_values(0)[0]
-        fe.set_fast_threshold(9); fe.set_orb_threshold(35)
-        assert fe.get_fast_threshold() == 9 and fe.get_orb_threshold() == 35
+        fe.set_fast_threshold(45); fe.set_orb_threshold(35)
+        assert fe.get_fast_threshold() == 45 and fe.get_orb_threshold() == 35
         fe.process_stereo(None, None, repeat=True)
         kl, kr, dl, dr, m = fe.get_values(0)
-        ol, odl, _ = orc.orb_extract(frames[0, 0], nfeatures=600, fast_threshold=9)
-        orr, odr, _ = orc.orb_extract(frames[0, 1], nfeatures=600, fast_threshold=9)
+        ol, odl, _ = orc.orb_extract(frames[0, 0], nfeatures=600, fast_threshold=45)
+        orr, odr, _ = orc.orb_extract(frames[0, 1], nfeatures=600, fast_threshold=45)
         _assert_keypoints_equal(kl, ol); _assert_keypoints_equal(kr, orr)
         om = orc.match_rowband(ol, odl, orr, odr, max_dist=35)
         assert np.array_equal(m["trainIdx"], om["trainIdx"]) and np.array_equal(m["distance"], om["distance"])
         assert np.all(m["distance"] <= 35)
-        assert not (len(k20) == len(kl) and np.array_equal(k20["x"], kl["x"]))
+        assert len(kl) < len(k20) == 600      # a FAST threshold of 45 starves the quota on this scene
     finally:
         fe.close()
 
@@ -204,7 +204,8 @@ def test_bow_transform_vector_query(mods, voc, scene_frames):
             res = db.query(q, 4); ores = orc.bow_query(voc, odb, q, 4)
             assert [r[0] for r in res] == [r[0] for r in ores]
             assert [r[1] for r in res] == [r[1] for r in ores]
-        assert db.query(sets[0], 4)[0] == (0, 1.0)
+        top = db.query(sets[0], 4)[0]
+        assert top[0] == 0 and abs(top[1] - 1.0) < 1e-12          # a keyframe is its own best match
     finally:
         db.close(); fe.close()
 
