@@ -133,6 +133,14 @@ int sfe_get_values(sfe_context* ctx, int pair,
 int sfe_download_batch(sfe_context* ctx, const sfe_keypoint** kps, const uint8_t** desc,
                        const sfe_dmatch** matches, const sfe_pair_counts** counts);
 
+/* Streaming form of sfe_process_batch_host + sfe_download_batch: submit enqueues H2D copy, all kernels and the
+ * D2H copy of the results on sfe_stream() and returns at once; wait blocks until they have landed in the
+ * context's pinned result buffers (same layout as sfe_download_batch).  Two contexts used alternately overlap
+ * one batch's PCIe traffic with the other's kernels.  `images` should be pinned (sfe_host_staging). */
+int sfe_submit_batch_host(sfe_context* ctx, const uint8_t* images, int npairs, size_t stride, size_t image_stride);
+int sfe_wait_batch(sfe_context* ctx, const sfe_keypoint** kps, const uint8_t** desc,
+                   const sfe_dmatch** matches, const sfe_pair_counts** counts);
+
 /* Debug/parity taps: copy one pyramid (blurred=0) or blurred (blurred=1) level of image `img`
  * (index 2*pair+side) to host, tightly packed w*h. */
 int sfe_get_level(sfe_context* ctx, int img, int level, int blurred, uint8_t* out);

@@ -9,7 +9,9 @@
 //                        pass, round-half-even -- cv::sepFilter2D since OpenCV 3.4 (what cv2 4.13's ORB
 //                        runs; pinned bit-exactly by tests/golden).
 // One launch covers all levels and images.  A CTA stages a 134x22 footprint with one 3-D TMA load;
-// the reflect-101 border is resolved by index remapping inside the tile (TMA zero-fills outside).
+// border tiles patch the reflect-101 halo inside shared memory (TMA zero-fills outside the image), so the
+// passes are branch-free: the fixed-point row pass is two DP4A per output on byte-permuted words, the
+// column pass works on 4x4 register blocks and stores packed 32-bit words.
 // HBM-bound: 1 byte read + 1 byte written per pixel.
 #include "sfe_internal.cuh"
 
@@ -18,13 +20,20 @@ __constant__ float c_taps_f[7];
 
 void sfe_upload_blur_taps(const float* taps) { cudaMemcpyToSymbol(c_taps_f, taps, 7 * sizeof(float)); }
 
+// Row pass of the fixed-point mode with DP4A: 7 taps = two dot products of 4 packed bytes.
+__device__ __forceinline__ int row7_dp4a(uint32_t lo4, uint32_t hi4)
+{
+    // taps 18 34 49 55 | 49 34 18 0, little-endian packed
+    return (int)__dp4a(hi4, 0x00122231u, __dp4a(lo4, 0x37312212u, 0u));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 blur_kernel(const __grid_constant__ LevelPack P, uint8_t* __restrict__ blur)
 {
     __shared__ alignas(128) uint8_t tile[BLUR_BOX_H * BLUR_BOX_W];
     __shared__ alignas(8) uint64_t bar;
-    __shared__ int rowbuf[BLUR_BOX_H * BLUR_TW];
+    __shared__ alignas(16) int rowbuf[22 * BLUR_TW];
 
     const int tid = threadIdx.x;
     int level = 0;
@@ -36,7 +45,7 @@ blur_kernel(const __grid_constant__ LevelPack P, uint8_t* __restrict__ blur)
     const int x0 = (t % g.btiles_x) * BLUR_TW, y0 = (t / g.btiles_x) * BLUR_TH;
     const int img = blockIdx.y;
     const int w = g.w, h = g.h;
-    const int bx0 = (x0 - 3) & ~15;               // TMA: box start must be 16-byte aligned in x
+    const int bx0 = x0 - 16;                      // TMA box start (16-byte aligned); tile byte 12 = pixel x0-4
 
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -46,58 +55,96 @@ blur_kernel(const __grid_constant__ LevelPack P, uint8_t* __restrict__ blur)
     }
     mbar_wait(&bar, 0);
 
-    // ---- row pass: rowbuf[r][x] for the 22 tile rows ---------------------------------------
-    for (int i = tid; i < BLUR_BOX_H * BLUR_TW; i += 256) {
-        const int r = i >> 7, x = i & 127;
-        int iy = y0 - 3 + r;                               // image row of this tile row (reflect-101)
-        iy = iy < 0 ? -iy : (iy >= h ? 2 * h - 2 - iy : iy);
-        const int tr = min(max(iy - (y0 - 3), 0), BLUR_BOX_H - 1);   // only rows feeding y >= h can clamp
-        const uint8_t* row = tile + tr * BLUR_BOX_W;
-        int acc_i = 0; float acc_f = 0.f;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            int ix = x0 + x - 3 + k;
-            ix = ix < 0 ? -ix : (ix >= w ? 2 * w - 2 - ix : ix);
-            int tx = ix - bx0;
-            tx = min(max(tx, 0), BLUR_BOX_W - 1);          // only padding columns (x >= w) can clamp
-            const int v = row[tx];
-            if (MODE == SFE_BLUR_CV24_FIXED) acc_i += c_taps_i[k] * v;
-            else acc_f = (k == 0) ? __fmul_rn(c_taps_f[0], (float)v) : __fadd_rn(acc_f, __fmul_rn(c_taps_f[k], (float)v));
+    // ---- reflect-101 fix-up, border tiles only (TMA zero-filled what lies outside the image) ----------
+    // tile row r <-> image row y0-3+r (r < 22 used); tile byte c <-> image column bx0+c
+    const bool bl = x0 == 0, br = x0 + BLUR_TW + 3 > w, bt = y0 == 0, bb = y0 + BLUR_TH + 3 > h;
+    if (bl || br) {                                // columns first (rows still raw)
+        for (int i = tid; i < 22 * 8; i += 256) {
+            const int r = i >> 3, k = i & 7;
+            uint8_t* row = tile + r * BLUR_BOX_W;
+            if (bl && k < 3) row[16 - 1 - k] = row[16 + 1 + k];                       // x = -1-k  <- x = 1+k
+            if (br && k >= 4 && k < 7) { const int x = w + (k - 4); const int c = x - bx0;   // x = w+j <- w-2-j
+                if (c >= 0 && c < BLUR_BOX_W) row[c] = row[min(max(2 * w - 2 - x - bx0, 0), BLUR_BOX_W - 1)]; }
         }
-        rowbuf[i] = (MODE == SFE_BLUR_CV24_FIXED) ? acc_i : __float_as_int(acc_f);
+        __syncthreads();
+    }
+    if (bt || bb) {
+        for (int i = tid; i < 6 * (BLUR_BOX_W / 4); i += 256) {
+            const int k = i / (BLUR_BOX_W / 4), cw = i - k * (BLUR_BOX_W / 4);
+            uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
+            if (bt && k < 3) tw[(3 - 1 - k) * (BLUR_BOX_W / 4) + cw] = tw[(3 + 1 + k) * (BLUR_BOX_W / 4) + cw];   // y = -1-k <- 1+k
+            if (bb && k >= 3) {
+                const int y = h + (k - 3), r = y - (y0 - 3), rs = 2 * h - 2 - y - (y0 - 3);
+                if (r >= 0 && r < 22 && rs >= 0) tw[r * (BLUR_BOX_W / 4) + cw] = tw[rs * (BLUR_BOX_W / 4) + cw];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- row pass: 4 adjacent outputs per thread from 3 aligned words ------------------------------------
+    {
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile) + 3;      // word 3 = pixels x0-4 .. x0-1
+        for (int i = tid; i < 22 * (BLUR_TW / 4); i += 256) {
+            const int r = i >> 5, q = i & 31;
+            const uint32_t* c = tw + r * (BLUR_BOX_W / 4) + q;
+            const uint32_t A = c[0], B = c[1], C = c[2];                       // pixels x-4..x-1 | x..x+3 | x+4..x+7
+            int4 o;
+            if (MODE == SFE_BLUR_CV24_FIXED) {
+                o.x = row7_dp4a(__byte_perm(A, B, 0x4321), __byte_perm(B, C, 0x4321));
+                o.y = row7_dp4a(__byte_perm(A, B, 0x5432), __byte_perm(B, C, 0x5432));
+                o.z = row7_dp4a(__byte_perm(A, B, 0x6543), __byte_perm(B, C, 0x6543));
+                o.w = row7_dp4a(B, C);
+            } else {
+                float px[10];
+                px[0] = (float)((A >> 8) & 0xff); px[1] = (float)((A >> 16) & 0xff); px[2] = (float)(A >> 24);
+                px[3] = (float)(B & 0xff); px[4] = (float)((B >> 8) & 0xff); px[5] = (float)((B >> 16) & 0xff); px[6] = (float)(B >> 24);
+                px[7] = (float)(C & 0xff); px[8] = (float)((C >> 8) & 0xff); px[9] = (float)((C >> 16) & 0xff);
+                float acc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = __fmul_rn(c_taps_f[0], px[e]);
+#pragma unroll
+                    for (int k = 1; k < 7; ++k) a = __fadd_rn(a, __fmul_rn(c_taps_f[k], px[e + k]));
+                    acc[e] = a;
+                }
+                o.x = __float_as_int(acc[0]); o.y = __float_as_int(acc[1]); o.z = __float_as_int(acc[2]); o.w = __float_as_int(acc[3]);
+            }
+            *reinterpret_cast<int4*>(rowbuf + r * BLUR_TW + 4 * q) = o;
+        }
     }
     __syncthreads();
 
-    // ---- column pass: 4 adjacent pixels per thread, one 32-bit store ------------------------
+    // ---- column pass: 4 columns x 4 rows per thread; one 32-bit store per row ---------------------------
     uint8_t* dst = blur + g.lvl_ofs + (size_t)img * g.img_bytes;
-    for (int i = tid; i < BLUR_TH * BLUR_TW / 4; i += 256) {
-        const int y = i >> 5, xq = (i & 31) * 4;
-        if (y0 + y >= h) continue;
-        uint32_t packed = 0;
+    for (int i = tid; i < (BLUR_TH / 4) * (BLUR_TW / 4); i += 256) {
+        const int yq = (i >> 5) * 4, xq = (i & 31) * 4;
+        int4 rv[10];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int x = xq + e;
-            int v;
-            if (MODE == SFE_BLUR_CV24_FIXED) {
-                int s = 0;
+        for (int k = 0; k < 10; ++k) rv[k] = *reinterpret_cast<const int4*>(rowbuf + (yq + k) * BLUR_TW + xq);
 #pragma unroll
-                for (int k = 0; k < 7; ++k) s += c_taps_i[k] * rowbuf[(y + k) * BLUR_TW + x];
-                s = (s + (1 << 15)) >> 16;
-                v = min(s, 255);
-            } else {
-                float s = __fmul_rn(c_taps_f[3], __int_as_float(rowbuf[(y + 3) * BLUR_TW + x]));
+        for (int yy = 0; yy < 4; ++yy) {
+            if (y0 + yq + yy >= h) break;
+            int v[4];
 #pragma unroll
-                for (int j = 1; j <= 3; ++j) {
-                    const float pr = __fadd_rn(__int_as_float(rowbuf[(y + 3 + j) * BLUR_TW + x]),
-                                               __int_as_float(rowbuf[(y + 3 - j) * BLUR_TW + x]));
-                    s = __fadd_rn(s, __fmul_rn(c_taps_f[3 + j], pr));
+            for (int e = 0; e < 4; ++e) {
+#define RV(k) (e == 0 ? rv[k].x : e == 1 ? rv[k].y : e == 2 ? rv[k].z : rv[k].w)
+                if (MODE == SFE_BLUR_CV24_FIXED) {
+                    int s = 55 * RV(yy + 3) + 49 * (RV(yy + 2) + RV(yy + 4)) + 34 * (RV(yy + 1) + RV(yy + 5)) + 18 * (RV(yy) + RV(yy + 6));
+                    s = (s + (1 << 15)) >> 16;
+                    v[e] = min(s, 255);
+                } else {
+                    float s = __fmul_rn(c_taps_f[3], __int_as_float(RV(yy + 3)));
+#pragma unroll
+                    for (int j = 1; j <= 3; ++j)
+                        s = __fadd_rn(s, __fmul_rn(c_taps_f[3 + j], __fadd_rn(__int_as_float(RV(yy + 3 + j)), __int_as_float(RV(yy + 3 - j)))));
+                    v[e] = min(max(__float2int_rn(s), 0), 255);
                 }
-                v = min(max(__float2int_rn(s), 0), 255);
+#undef RV
+                if (x0 + xq + e >= w) v[e] = 0;
             }
-            if (x0 + x >= w) v = 0;
-            packed |= (uint32_t)v << (8 * e);
+            *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + yq + yy) * g.pitch + x0 + xq) =
+                (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + y) * g.pitch + x0 + xq) = packed;
     }
 }
 

@@ -10,11 +10,13 @@
 //
 // One launch covers all levels and images: blockIdx.x -> (level, tile) through a prefix table,
 // blockIdx.y -> image.  A CTA stages its 136x24 pixel footprint with one 3-D TMA load, then:
-//   A. every thread runs the opposite-pair quick reject on its pixels and survivors are compacted
-//      into a shared candidate list with warp ballots;
-//   B. the compacted candidates get the exact 16-pixel test and, if corners, the arc score;
-//   C. 3x3 NMS on the shared score tile; survivors are appended to the per-(image,level) raw list
-//      with one warp-aggregated atomic per warp.
+//   A.  SWAR quick reject, 4 pixels per thread (VABSDIFF4 + byte-parallel compares) on the opposite
+//       pairs (0,8) and (4,12); survivors are compacted into a shared list (warp scan + one atomic);
+//   B1. exact FAST-9 test on the survivors: the 16 ring bytes are packed 4 per word, compared SWAR,
+//       folded to two 16-bit masks and tested for 9 contiguous bits; corners are compacted again;
+//   B2. arc score of the corners (sliding-window min/max), written to the shared score tile;
+//   C.  3x3 strict NMS evaluated only at the corners; survivors are appended to the per-(image,level)
+//       raw list with one warp-aggregated atomic per warp.
 // Integer-only; bounded by HBM reads of the level (1 byte/pixel) plus issue slots for the tests.
 #include "sfe_internal.cuh"
 
@@ -28,15 +30,37 @@ __device__ __forceinline__ int arc9_any(uint32_t m)      // m: 16-bit ring mask;
     return (x & 0xffffu) != 0;
 }
 
+// SWAR helpers on 4 packed bytes; flags are returned in bit 7 of each byte.
+__device__ __forceinline__ uint32_t gt80_const(uint32_t x, uint32_t k7f_minus_t)   // x > t per byte, t < 128
+{
+    return (((x & 0x7f7f7f7fu) + k7f_minus_t) | x) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t gt80(uint32_t a, uint32_t b)                   // a > b per byte (unsigned)
+{
+    // ge(b,a): low 7 bits compare through a borrow-free subtract, then the top bits decide
+    const uint32_t t = (b | 0x80808080u) - (a & 0x7f7f7f7fu);
+    const uint32_t ge = (b & ~a) | (~(a ^ b) & t);
+    return ~ge & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t nibble_of_flags(uint32_t f80)                  // bit 7 of byte i -> bit i
+{
+    return (f80 * 0x00204081u) >> 28;
+}
+
+#define FAST_WJ 34                       // score words per row: pixel columns tx0-4 .. tx0+131
+#define FAST_NPOS (FAST_SH * FAST_WJ * 4)
+#define FAST_TP (FAST_BOX_W / 4)         // tile pitch in words
+
 __global__ void __launch_bounds__(256)
 fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int32_t* __restrict__ raw_count,
             const int th)
 {
     __shared__ alignas(128) uint8_t tile[FAST_BOX_H * FAST_BOX_W];
     __shared__ alignas(8) uint64_t bar;
-    __shared__ uint8_t score[FAST_SH * FAST_SW];
-    __shared__ uint16_t cand[FAST_SH * 130];
-    __shared__ int ncand;
+    __shared__ alignas(16) uint8_t score[FAST_SH * FAST_WJ * 4];
+    __shared__ uint16_t list1[FAST_NPOS];       // quick-test survivors: (row*34 + word)*4 + byte
+    __shared__ uint16_t list2[FAST_NPOS];       // corners: same | polarity << 15
+    __shared__ int n1, n2;
 
     const int tid = threadIdx.x, lane = tid & 31;
     int level = 0;
@@ -45,77 +69,112 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
         if (l < P.nlevels && (int)blockIdx.x >= P.ftile_prefix[l]) level = l;
     const LevelGeom& g = P.g[level];
     const int t = blockIdx.x - P.ftile_prefix[level];
-    const int tx0 = g.rx0 + (t % g.ftiles_x) * FAST_TW;
+    const int tx0 = (g.rx0 & ~3) + (t % g.ftiles_x) * FAST_TW;     // multiple of 4: pixel words are smem words
     const int ty0 = g.ry0 + (t / g.ftiles_x) * FAST_TH;
     const int img = blockIdx.y;
-    const int bx0 = (tx0 - 4) & ~15;              // TMA: box start must be 16-byte aligned in x
-    const int xoff = tx0 - 4 - bx0;               // tile column of pixel tx0-4
+    const int bx0 = (tx0 - 8) & ~15;              // TMA: box start must be 16-byte aligned in x
+    const int xoff = tx0 - 8 - bx0;               // 0, 4, 8 or 12: tile byte column of pixel tx0-8
 
-    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); ncand = 0; }
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); n1 = 0; n2 = 0; }
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar, FAST_BOX_H * FAST_BOX_W);
         tma_load_3d(tile, &P.pyr_map[level], bx0, ty0 - 4, img, &bar);
     }
-    for (int i = tid; i < FAST_SH * FAST_SW / 4; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+    for (int i = tid; i < FAST_SH * FAST_WJ; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0u;
     mbar_wait(&bar, 0);
 
-    // ---- A: quick reject on the 130x18 score positions ------------------------------------
-    // score position (sx, sy) <-> pixel (tx0-1+sx, ty0-1+sy) <-> tile byte (sx+3+xoff, sy+3)
-    const int w = g.w, h = g.h;
-    for (int base = 0; base < FAST_SH * 130; base += 256) {
-        const int pos = base + tid;
-        bool pass = false;
-        if (pos < FAST_SH * 130) {
-            const int sy = pos / 130, sx = pos - sy * 130;
-            const int px = tx0 - 1 + sx, py = ty0 - 1 + sy;
-            if (px >= 3 && px < w - 3 && py >= 3 && py < h - 3) {
-                const uint8_t* c = tile + (sy + 3) * FAST_BOX_W + sx + 3 + xoff;
-                const int v = c[0];
-                const int lo = v - th, hi = v + th;
-                const int p0 = c[3 * FAST_BOX_W], p8 = c[-3 * FAST_BOX_W], p4 = c[3], p12 = c[-3];
-                // every 9-arc contains one pixel of each opposite pair
-                const bool br = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
-                const bool dk = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
-                pass = br || dk;
+    // score word (j, r) <-> pixels (tx0-4+4j .. +3, ty0-1+r) <-> tile word (xoff/4 + 1 + j, r+3)
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile) + (xoff >> 2) + 1;
+    const uint8_t* tb = tile + xoff + 4;
+
+    // ---- A: SWAR quick reject, 4 pixels per thread: every 9-arc holds one pixel of each opposite pair,
+    //         so a corner needs |p-v| > th on (0 or 8) and on (4 or 12) -------------------------------
+    const uint32_t kq = (uint32_t)(0x7f - th) * 0x01010101u;
+    for (int base = 0; base < FAST_SH * FAST_WJ; base += 256) {
+        const int idx = base + tid;
+        uint32_t m = 0;
+        if (idx < FAST_SH * FAST_WJ) {
+            const int r = idx / FAST_WJ, j = idx - r * FAST_WJ;
+            if (tx0 - 4 + 4 * j <= g.rx1 && ty0 - 1 + r <= g.ry1) {
+                const uint32_t* c = tw + (r + 3) * FAST_TP + j;
+                const uint32_t v = c[0];
+                const uint32_t a0 = __vabsdiffu4(c[3 * FAST_TP], v), a8 = __vabsdiffu4(c[-3 * FAST_TP], v);
+                const uint32_t a4 = __vabsdiffu4(__byte_perm(v, c[1], 0x6543), v);
+                const uint32_t a12 = __vabsdiffu4(__byte_perm(c[-1], v, 0x4321), v);
+                m = (gt80_const(a0, kq) | gt80_const(a8, kq)) & (gt80_const(a4, kq) | gt80_const(a12, kq));
             }
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
+        // warp-level compaction of the (up to 4) flagged bytes of each lane
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
             int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&ncand, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (pass) cand[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)pos;
+            if (lane == 31) wbase = atomicAdd(&n1, total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int o = wbase + incl - cnt;
+            uint32_t mm = m;
+            while (mm) {
+                const int b = (__ffs(mm) - 1) >> 3;
+                list1[o++] = (uint16_t)(idx * 4 + b);
+                mm &= mm - 1;
+            }
         }
     }
     __syncthreads();
 
-    // ---- B: exact test + score on the compacted candidates --------------------------------
-    const int nc = ncand;
-    for (int i = tid; i < nc; i += 256) {
-        const int pos = cand[i];
-        const int sy = pos / 130, sx = pos - sy * 130;
-        const uint8_t* c = tile + (sy + 3) * FAST_BOX_W + sx + 3 + xoff;
+    // ---- B1: exact FAST-9 test on the survivors; the 16 ring bytes are packed 4 per word and compared SWAR ----
+    const int nc1 = n1;
+    for (int base = 0; base < nc1; base += 256) {
+        const int i = base + tid;
+        bool corner = false; uint32_t entry = 0;
+        if (i < nc1) {
+            const int pos = list1[i];
+            const int wi = pos >> 2, r = wi / FAST_WJ, j = wi - r * FAST_WJ;
+            const uint8_t* c = tb + (r + 3) * FAST_BOX_W + 4 * j + (pos & 3);
+            const int v = c[0];
+            const uint32_t w0 = c[3 * FAST_BOX_W] | (c[3 * FAST_BOX_W + 1] << 8) | (c[2 * FAST_BOX_W + 2] << 16) | (c[FAST_BOX_W + 3] << 24);
+            const uint32_t w1 = c[3] | (c[-FAST_BOX_W + 3] << 8) | (c[-2 * FAST_BOX_W + 2] << 16) | (c[-3 * FAST_BOX_W + 1] << 24);
+            const uint32_t w2 = c[-3 * FAST_BOX_W] | (c[-3 * FAST_BOX_W - 1] << 8) | (c[-2 * FAST_BOX_W - 2] << 16) | (c[-FAST_BOX_W - 3] << 24);
+            const uint32_t w3 = c[-3] | (c[FAST_BOX_W - 3] << 8) | (c[2 * FAST_BOX_W - 2] << 16) | (c[3 * FAST_BOX_W - 1] << 24);
+            const uint32_t hi4 = (uint32_t)min(v + th, 255) * 0x01010101u, lo4 = (uint32_t)max(v - th, 0) * 0x01010101u;
+            const uint32_t mb = nibble_of_flags(gt80(w0, hi4)) | (nibble_of_flags(gt80(w1, hi4)) << 4) |
+                                (nibble_of_flags(gt80(w2, hi4)) << 8) | (nibble_of_flags(gt80(w3, hi4)) << 12);
+            const uint32_t md = nibble_of_flags(gt80(lo4, w0)) | (nibble_of_flags(gt80(lo4, w1)) << 4) |
+                                (nibble_of_flags(gt80(lo4, w2)) << 8) | (nibble_of_flags(gt80(lo4, w3)) << 12);
+            const bool isb = arc9_any(mb);
+            corner = isb || arc9_any(md);
+            entry = (uint32_t)pos | (isb ? 0x8000u : 0u);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+        if (bal) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&n2, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (corner) list2[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)entry;
+        }
+    }
+    __syncthreads();
+
+    // ---- B2: corner score = (max over the 16 arcs of the min over the arc of +-(ring - centre)) - 1 -----------
+    const int nc2 = n2;
+    for (int i = tid; i < nc2; i += 256) {
+        const int e16 = list2[i];
+        const int pos = e16 & 0x7fff;
+        const int wi = pos >> 2, r = wi / FAST_WJ, j = wi - r * FAST_WJ;
+        const uint8_t* c = tb + (r + 3) * FAST_BOX_W + 4 * j + (pos & 3);
         const int v = c[0];
-        int d[16];
-        d[0] = c[3 * FAST_BOX_W] - v;       d[1] = c[3 * FAST_BOX_W + 1] - v;
-        d[2] = c[2 * FAST_BOX_W + 2] - v;   d[3] = c[FAST_BOX_W + 3] - v;
-        d[4] = c[3] - v;                    d[5] = c[-FAST_BOX_W + 3] - v;
-        d[6] = c[-2 * FAST_BOX_W + 2] - v;  d[7] = c[-3 * FAST_BOX_W + 1] - v;
-        d[8] = c[-3 * FAST_BOX_W] - v;      d[9] = c[-3 * FAST_BOX_W - 1] - v;
-        d[10] = c[-2 * FAST_BOX_W - 2] - v; d[11] = c[-FAST_BOX_W - 3] - v;
-        d[12] = c[-3] - v;                  d[13] = c[FAST_BOX_W - 3] - v;
-        d[14] = c[2 * FAST_BOX_W - 2] - v;  d[15] = c[3 * FAST_BOX_W - 1] - v;
-        uint32_t mb = 0, md = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(d[k] > th) << k; md |= (uint32_t)(d[k] < -th) << k; }
-        const bool isb = arc9_any(mb), isd = arc9_any(md);
-        if (!(isb || isd)) continue;
-        // strength of the passing polarity (the other one cannot also hold a 9-arc):
-        // max over arcs of the min over the arc of e[k] = +-d[k]  (sliding-window min, window 9)
+        const int sg = (e16 & 0x8000) ? 1 : -1;
         int e[16];
+        e[0] = c[3 * FAST_BOX_W];       e[1] = c[3 * FAST_BOX_W + 1];   e[2] = c[2 * FAST_BOX_W + 2];   e[3] = c[FAST_BOX_W + 3];
+        e[4] = c[3];                    e[5] = c[-FAST_BOX_W + 3];      e[6] = c[-2 * FAST_BOX_W + 2];  e[7] = c[-3 * FAST_BOX_W + 1];
+        e[8] = c[-3 * FAST_BOX_W];      e[9] = c[-3 * FAST_BOX_W - 1];  e[10] = c[-2 * FAST_BOX_W - 2]; e[11] = c[-FAST_BOX_W - 3];
+        e[12] = c[-3];                  e[13] = c[FAST_BOX_W - 3];      e[14] = c[2 * FAST_BOX_W - 2];  e[15] = c[3 * FAST_BOX_W - 1];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = isb ? d[k] : -d[k];
+        for (int k = 0; k < 16; ++k) e[k] = sg * (e[k] - v);
         int m2[16], m4[16], best = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) m2[k] = min(e[k], e[(k + 1) & 15]);
@@ -126,23 +185,28 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
             const int m8 = min(m4[k], m4[(k + 4) & 15]);
             best = max(best, min(m8, e[(k + 8) & 15]));
         }
-        score[sy * FAST_SW + sx] = (uint8_t)(best - 1);
+        score[pos] = (uint8_t)(best - 1);
     }
     __syncthreads();
 
-    // ---- C: 3x3 strict NMS + emit ----------------------------------------------------------
+    // ---- C: 3x3 strict NMS, only at the corners, + emit ----------------------------------------------------
     int32_t* cnt = raw_count + (size_t)img * P.nlevels + level;
     uint32_t* out = raw + (size_t)img * P.raw_img_stride + g.raw_ofs;
-    for (int base = 0; base < FAST_TW * FAST_TH; base += 256) {
-        const int pos = base + tid;
-        const int oy = pos >> 7, ox = pos & 127;
-        const int px = tx0 + ox, py = ty0 + oy;
-        const uint8_t* s = score + (oy + 1) * FAST_SW + ox + 1;
-        const int sc = s[0];
-        bool keep = false;
-        if (sc != 0 && px < g.rx1 && py < g.ry1) {
-            keep = sc > s[-1] && sc > s[1] && sc > s[-FAST_SW - 1] && sc > s[-FAST_SW] && sc > s[-FAST_SW + 1] &&
-                   sc > s[FAST_SW - 1] && sc > s[FAST_SW] && sc > s[FAST_SW + 1];
+    const int SPB = FAST_WJ * 4;
+    const int y_end = min(ty0 + FAST_TH, g.ry1);
+    for (int base = 0; base < nc2; base += 256) {
+        const int i = base + tid;
+        bool keep = false; int px = 0, py = 0, sc = 0;
+        if (i < nc2) {
+            const int pos = list2[i] & 0x7fff;
+            const int r = pos / SPB, cb = pos - r * SPB;
+            px = tx0 - 4 + cb; py = ty0 - 1 + r;
+            if (px >= max(tx0, g.rx0) && px < min(tx0 + FAST_TW, g.rx1) && py >= ty0 && py < y_end) {
+                const uint8_t* s = score + pos;
+                sc = s[0];
+                keep = sc > s[-1] && sc > s[1] && sc > s[-SPB - 1] && sc > s[-SPB] && sc > s[-SPB + 1] &&
+                       sc > s[SPB - 1] && sc > s[SPB] && sc > s[SPB + 1];
+            }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         if (bal) {

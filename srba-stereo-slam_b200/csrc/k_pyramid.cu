@@ -73,3 +73,27 @@ void launch_pyramid_level(sfe_context* c, int level, int nimg)
     pyramid_kernel<<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
     c->launches++;
 }
+
+// ---- level 0 ingest: tightly packed host layout [img][H][W] -> pitched level-0 arena -----------------------
+// One linear H2D copy followed by this kernel replaces a row-by-row pitched DMA (W = 1241 is not a multiple of
+// 16, which the TMA descriptors of the consumers require of the row stride).
+__global__ void __launch_bounds__(256)
+unpack_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ dst, int w, int h, int pitch, size_t dimg_bytes)
+{
+    const int y = blockIdx.y, img = blockIdx.z;
+    const int x = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x >= pitch) return;
+    const uint8_t* src = packed + ((size_t)img * h + y) * w;
+    uint32_t v = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (x + e < w) v |= (uint32_t)__ldg(src + x + e) << (8 * e);
+    *reinterpret_cast<uint32_t*>(dst + (size_t)img * dimg_bytes + (size_t)y * pitch + x) = v;
+}
+
+void launch_unpack(sfe_context* c, int nimg)
+{
+    const LevelGeom& g = c->pack.g[0];
+    dim3 grid((g.pitch / 4 + 255) / 256, g.h, nimg);
+    unpack_kernel<<<grid, 256, 0, c->stream>>>(c->d_packed, c->d_pyr + g.lvl_ofs, g.w, g.h, g.pitch, g.img_bytes);
+    c->launches++;
+}

@@ -82,7 +82,7 @@ static int create_impl(sfe_context* c)
     if (!(f.scale_factor >= 1.05f && f.scale_factor <= 1.25f)) { c->err = "scale_factor must be in [1.05,1.25] (tile footprint)"; return SFE_ERR_INVALID; }
     if (f.edge_threshold < 19 || f.edge_threshold > 200) { c->err = "edge_threshold must be in [19,200] (rBRIEF reach)"; return SFE_ERR_INVALID; }
     if (f.max_pairs < 1 || f.max_pairs > 16384) { c->err = "max_pairs must be in [1,16384]"; return SFE_ERR_INVALID; }
-    if (f.fast_threshold < 1 || f.fast_threshold > 254) { c->err = "fast_threshold must be in [1,254]"; return SFE_ERR_INVALID; }
+    if (f.fast_threshold < 1 || f.fast_threshold > 127) { c->err = "fast_threshold must be in [1,127]"; return SFE_ERR_INVALID; }
     if (f.blur_mode != SFE_BLUR_CV24_FIXED && f.blur_mode != SFE_BLUR_FLOAT) { c->err = "bad blur_mode"; return SFE_ERR_INVALID; }
 
     int ndev = 0;
@@ -127,7 +127,7 @@ static int create_impl(sfe_context* c)
         g.rx0 = m; g.ry0 = m; g.rx1 = g.w - m; g.ry1 = g.h - m;
         const int rw = std::max(g.rx1 - g.rx0, 0), rh = std::max(g.ry1 - g.ry0, 0);
         if (rw == 0 || rh == 0 || g.w < 16 || g.h < 16) { g.rx1 = g.rx0; g.ry1 = g.ry0; g.ftiles_x = g.ftiles_y = 0; }
-        else { g.ftiles_x = (rw + FAST_TW - 1) / FAST_TW; g.ftiles_y = (rh + FAST_TH - 1) / FAST_TH; }
+        else { g.ftiles_x = (g.rx1 - (g.rx0 & ~3) + FAST_TW - 1) / FAST_TW; g.ftiles_y = (rh + FAST_TH - 1) / FAST_TH; }   // tile origin is 4-aligned
         g.btiles_x = (g.w + BLUR_TW - 1) / BLUR_TW; g.btiles_y = (g.h + BLUR_TH - 1) / BLUR_TH;
         g.raw_cap = std::max(((rw + 1) / 2) * ((rh + 1) / 2), 1);      // NMS: no two 8-adjacent maxima
         g.raw_ofs = raw_ofs; raw_ofs += g.raw_cap;
@@ -251,7 +251,7 @@ extern "C" void sfe_destroy(sfe_context* c)
     cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_raw); cudaFree(c->d_raw_count);
     cudaFree(c->d_sel_xy); cudaFree(c->d_sel_resp); cudaFree(c->d_sel_count); cudaFree(c->d_kp); cudaFree(c->d_desc);
     cudaFree(c->d_kp_count); cudaFree(c->d_matches); cudaFree(c->d_match_count); cudaFree(c->d_status);
-    cudaFree(c->d_bf_q); cudaFree(c->d_bf_t); cudaFree(c->d_bf_best); cudaFree(c->d_bf_ofs);
+    cudaFree(c->d_packed); cudaFree(c->d_bf_q); cudaFree(c->d_bf_t); cudaFree(c->d_bf_best); cudaFree(c->d_bf_ofs);
     for (int l = 0; l < SFE_MAX_LEVELS; ++l) { cudaFree(c->d_xtab[l]); cudaFree(c->d_ytab[l]); }
     cudaFreeHost(c->h_images); cudaFreeHost(c->h_kp); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_matches);
     cudaFreeHost(c->h_kp_count); cudaFreeHost(c->h_match_count); cudaFreeHost(c->h_status); cudaFreeHost(c->h_counts);
@@ -265,7 +265,7 @@ extern "C" void sfe_destroy(sfe_context* c)
 // ---- thresholds -----------------------------------------------------------------------------------
 extern "C" int sfe_set_fast_threshold(sfe_context* c, int th)
 {
-    if (!c || th < 1 || th > 254) return SFE_ERR_INVALID;
+    if (!c || th < 1 || th > 127) return SFE_ERR_INVALID;
     if (th != c->fast_th) { c->fast_th = th; for (auto& g : c->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; } }
     return SFE_OK;
 }
@@ -340,6 +340,13 @@ static int upload(sfe_context* c, const uint8_t* images, int npairs, size_t stri
     if (!images || npairs < 1 || npairs > c->cfg.max_pairs) { c->err = "bad upload arguments"; return SFE_ERR_INVALID; }
     const LevelGeom& g = c->pack.g[0];
     if (stride < (size_t)g.w || image_stride < stride * (size_t)(g.h - 1) + g.w) { c->err = "bad strides"; return SFE_ERR_INVALID; }
+    if (stride == (size_t)g.w && image_stride == (size_t)g.w * g.h) {
+        // tightly packed: one linear DMA, then a kernel spreads the rows onto the pitched level-0 arena
+        if (!c->d_packed) SFE_CUDA(c, dalloc(&c->d_packed, (size_t)c->NI * g.w * g.h));
+        SFE_CUDA(c, cudaMemcpyAsync(c->d_packed, images, (size_t)2 * npairs * g.w * g.h, cudaMemcpyHostToDevice, c->stream));
+        launch_unpack(c, 2 * npairs);
+        return SFE_OK;
+    }
     // one strided 3-D copy: rows of w bytes, h rows, 2*npairs images
     cudaMemcpy3DParms p = {};
     if (image_stride % stride == 0) {
@@ -463,6 +470,55 @@ extern "C" int sfe_get_values(sfe_context* c, int pair, sfe_keypoint* kl, sfe_ke
     if (m) SFE_CUDA(c, cudaMemcpyAsync(m, c->d_matches + (size_t)pair * cap, sizeof(sfe_dmatch) * pc.n_matches, cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
     if (counts) *counts = pc;
+    return SFE_OK;
+}
+
+static int enqueue_download(sfe_context* c)
+{
+    const int np = c->last_npairs; const size_t cap = c->pack.kp_cap;
+    SFE_CUDA(c, cudaMemcpyAsync(c->h_kp, c->d_kp, sizeof(sfe_keypoint) * 2 * np * cap, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc, 32 * 2 * (size_t)np * cap, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(c, cudaMemcpyAsync(c->h_matches, c->d_matches, sizeof(sfe_dmatch) * np * cap, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(c, cudaMemcpyAsync(c->h_kp_count, c->d_kp_count, sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(c, cudaMemcpyAsync(c->h_match_count, c->d_match_count, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, c->stream));
+    return SFE_OK;
+}
+
+static void fill_counts(sfe_context* c)
+{
+    for (int p = 0; p < c->last_npairs; ++p) {
+        c->h_counts[p].n_left = c->h_kp_count[2 * p]; c->h_counts[p].n_right = c->h_kp_count[2 * p + 1];
+        c->h_counts[p].n_matches = c->h_match_count[p];
+        c->h_counts[p].status = (c->h_status[2 * p] | c->h_status[2 * p + 1]) ? SFE_ERR_CAPACITY : SFE_OK;
+    }
+}
+
+extern "C" int sfe_submit_batch_host(sfe_context* c, const uint8_t* images, int npairs, size_t stride, size_t image_stride)
+{
+    if (!c) return SFE_ERR_INVALID;
+    int r = upload(c, images, npairs, stride, image_stride);
+    if (r) return r;
+    r = run_batch(c, npairs);
+    if (r) return r;
+    return enqueue_download(c);
+}
+
+extern "C" int sfe_wait_batch(sfe_context* c, const sfe_keypoint** kps, const uint8_t** desc, const sfe_dmatch** matches,
+                              const sfe_pair_counts** counts)
+{
+    if (!c) return SFE_ERR_INVALID;
+    if (!c->have_results) { c->err = "no batch in flight"; return SFE_ERR_STATE; }
+    SFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    fill_counts(c);
+    if (kps) *kps = c->h_kp; if (desc) *desc = c->h_desc; if (matches) *matches = c->h_matches; if (counts) *counts = c->h_counts;
+    c->downloaded = true;
+    for (int p = 0; p < c->last_npairs; ++p)
+        if (c->h_counts[p].status) {
+            c->err = "a device-side list overflowed (raise capacities / lower nfeatures)";
+            cudaMemsetAsync(c->d_status, 0, sizeof(int32_t) * c->NI, c->stream);
+            return SFE_ERR_CAPACITY;
+        }
     return SFE_OK;
 }
 

@@ -22,7 +22,6 @@
 #define FAST_TH 16
 #define FAST_BOX_W 160
 #define FAST_BOX_H 24
-#define FAST_SW 132        // score tile pitch (130 used)
 #define FAST_SH 18
 // Blur: 128x16 output tile, halo 3 -> 134x22 used of a 160x24 box.
 #define BLUR_TW 128
@@ -131,6 +130,7 @@ struct sfe_context {
     int32_t* d_status = nullptr;             // [NI] device-side error flags (capacity overflow)
     // pinned staging
     uint8_t* h_images = nullptr; size_t h_images_bytes = 0;
+    uint8_t* d_packed = nullptr;             // tightly packed upload staging [NI][H][W]
     sfe_keypoint* h_kp = nullptr; uint8_t* h_desc = nullptr; sfe_dmatch* h_matches = nullptr;
     int32_t* h_kp_count = nullptr; int32_t* h_match_count = nullptr; int32_t* h_status = nullptr;
     sfe_pair_counts* h_counts = nullptr;
@@ -166,5 +166,6 @@ void prepare_rowband(sfe_context* c);
 void launch_blur(sfe_context* c, int nimg);
 void launch_describe(sfe_context* c, int nimg);
 void launch_match_rowband(sfe_context* c, int npairs);
+void launch_unpack(sfe_context* c, int nimg);
 void launch_match_bf(cudaStream_t s, const uint8_t* d_query, const int32_t* d_q_ofs, const uint8_t* d_train,
                      const int32_t* d_t_ofs, int npairs, int max_nq, uint32_t* d_best);

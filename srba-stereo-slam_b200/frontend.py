@@ -71,6 +71,8 @@ def load_library():
     L.sfe_get_counts.argtypes = [vp, i32, vp]
     L.sfe_get_values.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.sfe_download_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.sfe_submit_batch_host.argtypes = [vp, vp, i32, sz, sz]
+    L.sfe_wait_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.sfe_get_level.argtypes = [vp, i32, i32, i32, vp]
     L.sfe_get_raw_corners.argtypes = [vp, i32, i32, vp, i32, vp]
     L.sfe_device_results.argtypes = [vp] + [C.POINTER(vp)] * 5
@@ -178,6 +180,19 @@ class StereoFrontEnd:
         n = C.c_size_t()
         p = self.lib.sfe_host_staging(self.h, C.byref(n))
         self._chk(self.lib.sfe_process_batch_host(self.h, p, npairs, self.cfg.width, self.cfg.width * self.cfg.height))
+
+    def submit_staged(self, npairs):
+        """Asynchronous: H2D from pinned staging + kernels + D2H of the results (sfe_submit_batch_host)."""
+        n = C.c_size_t()
+        p = self.lib.sfe_host_staging(self.h, C.byref(n))
+        self._chk(self.lib.sfe_submit_batch_host(self.h, p, npairs, self.cfg.width, self.cfg.width * self.cfg.height))
+
+    def wait_batch(self):
+        """Block until the submitted batch's results are in pinned host memory; returns numpy views
+        (keypoints [2*npairs, cap], descriptors [2*npairs, cap, 32], matches [npairs, cap], counts [npairs])."""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        self._chk(self.lib.sfe_wait_batch(self.h, *[C.byref(p) for p in ptrs]))
+        return ptrs
 
     def upload(self, images):
         images = np.ascontiguousarray(images, np.uint8).reshape(-1, self.cfg.height, self.cfg.width)
