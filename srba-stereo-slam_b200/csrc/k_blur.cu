@@ -29,20 +29,16 @@ __device__ __forceinline__ int row7_dp4a(uint32_t lo4, uint32_t hi4)
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-blur_kernel(const __grid_constant__ LevelPack P, uint8_t* __restrict__ blur)
+blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint8_t* __restrict__ blur)
 {
     __shared__ alignas(128) uint8_t tile[BLUR_BOX_H * BLUR_BOX_W];
     __shared__ alignas(8) uint64_t bar;
     __shared__ alignas(16) int rowbuf[22 * BLUR_TW];
 
     const int tid = threadIdx.x;
-    int level = 0;
-#pragma unroll
-    for (int l = 1; l < SFE_MAX_LEVELS; ++l)
-        if (l < P.nlevels && (int)blockIdx.x >= P.btile_prefix[l]) level = l;
+    const int4 ti = __ldg(tile_tab + blockIdx.x);
+    const int level = ti.x, x0 = ti.y, y0 = ti.z;
     const LevelGeom& g = P.g[level];
-    const int t = blockIdx.x - P.btile_prefix[level];
-    const int x0 = (t % g.btiles_x) * BLUR_TW, y0 = (t / g.btiles_x) * BLUR_TH;
     const int img = blockIdx.y;
     const int w = g.w, h = g.h;
     const int bx0 = x0 - 16;                      // TMA box start (16-byte aligned); tile byte 12 = pixel x0-4
@@ -152,7 +148,7 @@ void launch_blur(sfe_context* c, int nimg)
 {
     const int ntiles = c->pack.btile_prefix[c->pack.nlevels];
     dim3 grid(ntiles, nimg);
-    if (c->cfg.blur_mode == SFE_BLUR_FLOAT) blur_kernel<SFE_BLUR_FLOAT><<<grid, 256, 0, c->stream>>>(c->pack, c->d_blur);
-    else blur_kernel<SFE_BLUR_CV24_FIXED><<<grid, 256, 0, c->stream>>>(c->pack, c->d_blur);
+    if (c->cfg.blur_mode == SFE_BLUR_FLOAT) blur_kernel<SFE_BLUR_FLOAT><<<grid, 256, 0, c->stream>>>(c->pack, c->d_btile_tab, c->d_blur);
+    else blur_kernel<SFE_BLUR_CV24_FIXED><<<grid, 256, 0, c->stream>>>(c->pack, c->d_btile_tab, c->d_blur);
     c->launches++;
 }

@@ -52,8 +52,8 @@ __device__ __forceinline__ uint32_t nibble_of_flags(uint32_t f80)               
 #define FAST_TP (FAST_BOX_W / 4)         // tile pitch in words
 
 __global__ void __launch_bounds__(256)
-fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int32_t* __restrict__ raw_count,
-            const int th)
+fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint32_t* __restrict__ raw,
+            int32_t* __restrict__ raw_count, const int th)
 {
     __shared__ alignas(128) uint8_t tile[FAST_BOX_H * FAST_BOX_W];
     __shared__ alignas(8) uint64_t bar;
@@ -63,14 +63,9 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
     __shared__ int n1, n2;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    int level = 0;
-#pragma unroll
-    for (int l = 1; l < SFE_MAX_LEVELS; ++l)
-        if (l < P.nlevels && (int)blockIdx.x >= P.ftile_prefix[l]) level = l;
+    const int4 ti = __ldg(tile_tab + blockIdx.x);
+    const int level = ti.x, tx0 = ti.y, ty0 = ti.z;                 // tx0 is a multiple of 4: pixel words are smem words
     const LevelGeom& g = P.g[level];
-    const int t = blockIdx.x - P.ftile_prefix[level];
-    const int tx0 = (g.rx0 & ~3) + (t % g.ftiles_x) * FAST_TW;     // multiple of 4: pixel words are smem words
-    const int ty0 = g.ry0 + (t / g.ftiles_x) * FAST_TH;
     const int img = blockIdx.y;
     const int bx0 = (tx0 - 8) & ~15;              // TMA: box start must be 16-byte aligned in x
     const int xoff = tx0 - 8 - bx0;               // 0, 4, 8 or 12: tile byte column of pixel tx0-8
@@ -91,22 +86,26 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
     // ---- A: SWAR quick reject, 4 pixels per thread: every 9-arc holds one pixel of each opposite pair,
     //         so a corner needs |p-v| > th on (0 or 8) and on (4 or 12) -------------------------------
     const uint32_t kq = (uint32_t)(0x7f - th) * 0x01010101u;
-    for (int base = 0; base < FAST_SH * FAST_WJ; base += 256) {
-        const int idx = base + tid;
-        uint32_t m = 0;
-        if (idx < FAST_SH * FAST_WJ) {
-            const int r = idx / FAST_WJ, j = idx - r * FAST_WJ;
-            if (tx0 - 4 + 4 * j <= g.rx1 && ty0 - 1 + r <= g.ry1) {
-                const uint32_t* c = tw + (r + 3) * FAST_TP + j;
-                const uint32_t v = c[0];
-                const uint32_t a0 = __vabsdiffu4(c[3 * FAST_TP], v), a8 = __vabsdiffu4(c[-3 * FAST_TP], v);
-                const uint32_t a4 = __vabsdiffu4(__byte_perm(v, c[1], 0x6543), v);
-                const uint32_t a12 = __vabsdiffu4(__byte_perm(c[-1], v, 0x4321), v);
-                m = (gt80_const(a0, kq) | gt80_const(a8, kq)) & (gt80_const(a4, kq) | gt80_const(a12, kq));
+    {
+        uint32_t m[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = tid + 256 * k;
+            m[k] = 0;
+            if (idx < FAST_SH * FAST_WJ) {
+                const int r = idx / FAST_WJ, j = idx - r * FAST_WJ;
+                if (tx0 - 4 + 4 * j <= g.rx1 && ty0 - 1 + r <= g.ry1) {
+                    const uint32_t* c = tw + (r + 3) * FAST_TP + j;
+                    const uint32_t v = c[0];
+                    const uint32_t a0 = __vabsdiffu4(c[3 * FAST_TP], v), a8 = __vabsdiffu4(c[-3 * FAST_TP], v);
+                    const uint32_t a4 = __vabsdiffu4(__byte_perm(v, c[1], 0x6543), v);
+                    const uint32_t a12 = __vabsdiffu4(__byte_perm(c[-1], v, 0x4321), v);
+                    m[k] = (gt80_const(a0, kq) | gt80_const(a8, kq)) & (gt80_const(a4, kq) | gt80_const(a12, kq));
+                }
             }
         }
-        // warp-level compaction of the (up to 4) flagged bytes of each lane
-        const int cnt = __popc(m);
+        // one warp-level compaction for the (up to 12) flagged bytes of each lane
+        const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -116,11 +115,12 @@ fast_kernel(const __grid_constant__ LevelPack P, uint32_t* __restrict__ raw, int
             if (lane == 31) wbase = atomicAdd(&n1, total);
             wbase = __shfl_sync(0xffffffffu, wbase, 31);
             int o = wbase + incl - cnt;
-            uint32_t mm = m;
-            while (mm) {
-                const int b = (__ffs(mm) - 1) >> 3;
-                list1[o++] = (uint16_t)(idx * 4 + b);
-                mm &= mm - 1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int idx4 = (tid + 256 * k) * 4;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (m[k] & (0x80u << (8 * b))) list1[o++] = (uint16_t)(idx4 + b);
             }
         }
     }
@@ -226,6 +226,6 @@ void launch_fast(sfe_context* c, int nimg)
     const int ntiles = c->pack.ftile_prefix[c->pack.nlevels];
     if (ntiles == 0) return;
     dim3 grid(ntiles, nimg);
-    fast_kernel<<<grid, 256, 0, c->stream>>>(c->pack, c->d_raw, c->d_raw_count, c->fast_th);
+    fast_kernel<<<grid, 256, 0, c->stream>>>(c->pack, c->d_ftile_tab, c->d_raw, c->d_raw_count, c->fast_th);
     c->launches++;
 }

@@ -8,23 +8,30 @@
 //
 // One CTA = one 128x16 destination tile of one image.  Its source footprint (<= 176x24 u8 incl. alignment slack) is
 // fetched with a single 3-D TMA load (out-of-bounds rows/columns arrive as zeros and are never
-// weighted).  HBM-bound by design: per destination pixel ~1.44 source bytes read + 1 byte written.
+// weighted).  The horizontal pass runs once per SOURCE row on word loads: a funnel shift aligns the
+// footprint of 4 destination columns, two PRMTs gather the (left,right) byte pairs and DP2A applies the
+// 11-bit coefficients; the vertical pass is two IMAD.HI per pixel on the u16 intermediates.
+// Per destination pixel ~1.44 source bytes read + 1 byte written.
 #include "sfe_internal.cuh"
 
 struct PyrArgs {
     uint8_t* dst; int dpitch; size_t dimg_bytes;
     int dw, dh, sh;
-    const int2* xtab; const int2* ytab;
+    const uint32_t* gtab;       // per group of 4 destination columns: {src base, byte selectors, 4 x (a0 | a1<<16)}, 6 words
+    const int2* ytab;           // per destination row: {src row, b0 | b1<<16}
 };
+
+#define PYR_TPW (PYR_BOX_W / 4)      // tile pitch in words
 
 __global__ void __launch_bounds__(256)
 pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
 {
-    __shared__ alignas(128) uint8_t tile[PYR_BOX_H * PYR_BOX_W];
+    __shared__ alignas(128) uint32_t tile[PYR_BOX_H * PYR_TPW + 4];     // +4: the funnel may touch one word past the box
     __shared__ alignas(8) uint64_t bar;
+    __shared__ alignas(16) uint32_t hbuf[PYR_BOX_H * (PYR_TW / 2)];     // horizontal pass >> 4, two u16 per word
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PYR_TW, y0 = blockIdx.y * PYR_TH, img = blockIdx.z;
-    const int sx0 = a.xtab[x0].x;
+    const int sx0 = (int)a.gtab[(x0 >> 2) * 6];
     const int bx0 = sx0 & ~15;                    // TMA: box start must be 16-byte aligned in x
     const int sy0 = max(a.ytab[y0].x, 0);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
@@ -33,33 +40,51 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
         mbar_arrive_expect_tx(&bar, PYR_BOX_H * PYR_BOX_W);
         tma_load_3d(tile, &src_map, bx0, sy0, img, &bar);
     }
-    // while the tile is in flight: this thread's 8 destination columns and its row
-    const int tx = (tid & 15) * 8, ty = tid >> 4;
-    const int dy = y0 + ty;
-    int2 xt[8];
+    // while the tile is in flight: this thread's column group (4 destination columns) and its rows
+    const int gq = tid & 31, rr = tid >> 5;
+    const int q = min((x0 >> 2) + gq, ((a.dw + 3) >> 2) - 1);
+    const uint32_t* ge = a.gtab + (size_t)q * 6;
+    const int off = (int)__ldg(ge) - bx0;
+    const uint32_t sel = __ldg(ge + 1);
+    const uint32_t c0 = __ldg(ge + 2), c1 = __ldg(ge + 3), c2 = __ldg(ge + 4), c3 = __ldg(ge + 5);
+    const int wi = off >> 2, sh = (off & 3) * 8;
+    int2 yt[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xt[i] = a.xtab[min(x0 + tx + i, a.dw - 1)];
-    const int2 yt = a.ytab[min(dy, a.dh - 1)];
+    for (int k = 0; k < 2; ++k) yt[k] = a.ytab[min(y0 + rr + 8 * k, a.dh - 1)];
     mbar_wait(&bar, 0);
-    if (dy >= a.dh) return;
-    const int r0 = min(max(yt.x, 0), a.sh - 1) - sy0;
-    const int r1 = min(max(yt.x + 1, 0), a.sh - 1) - sy0;
-    const int b0 = (short)(yt.y & 0xffff), b1 = (short)(yt.y >> 16);
-    const uint8_t* S0 = tile + r0 * PYR_BOX_W;
-    const uint8_t* S1 = tile + r1 * PYR_BOX_W;
-    uint32_t out[2] = { 0u, 0u };
+
+    // ---- horizontal pass, once per source row: h = S[sx]*a0 + S[sx+1]*a1 (DP2A), stored as (h >> 4) in u16 ----
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int sx = xt[i].x - bx0;
-        const int a0 = (short)(xt[i].y & 0xffff), a1 = (short)(xt[i].y >> 16);
-        const int h0 = S0[sx] * a0 + S0[sx + 1] * a1;
-        const int h1 = S1[sx] * a0 + S1[sx + 1] * a1;
-        int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        if (x0 + tx + i >= a.dw) v = 0;             // keep the pitch padding deterministic
-        out[i >> 2] |= (uint32_t)(v & 0xff) << (8 * (i & 3));
+    for (int k = 0; k < 3; ++k) {
+        const int r = rr + 8 * k;
+        const uint32_t* row = tile + r * PYR_TPW + wi;
+        const uint32_t A = __funnelshift_r(row[0], row[1], sh), B = __funnelshift_r(row[1], row[2], sh);
+        const uint32_t b01 = __byte_perm(A, B, sel & 0xffffu), b23 = __byte_perm(A, B, sel >> 16);
+        const uint32_t h0 = __dp2a_lo(c0, b01, 0u) >> 4, h1 = __dp2a_hi(c1, b01, 0u) >> 4;
+        const uint32_t h2 = __dp2a_lo(c2, b23, 0u) >> 4, h3 = __dp2a_hi(c3, b23, 0u) >> 4;
+        *reinterpret_cast<uint2*>(hbuf + r * (PYR_TW / 2) + 2 * gq) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     }
-    uint8_t* D = a.dst + (size_t)img * a.dimg_bytes + (size_t)dy * a.dpitch + x0 + tx;
-    *reinterpret_cast<uint2*>(D) = make_uint2(out[0], out[1]);
+    __syncthreads();
+
+    // ---- vertical pass: (((b0*r0) >> 16) + ((b1*r1) >> 16) + 2) >> 2, 4 pixels per 32-bit store --------------
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int dy = y0 + rr + 8 * k;
+        if (dy >= a.dh) break;
+        const int r0 = min(max(yt[k].x, 0), a.sh - 1) - sy0;
+        const int r1 = min(max(yt[k].x + 1, 0), a.sh - 1) - sy0;
+        const uint32_t b0 = (uint32_t)(yt[k].y & 0xffff) << 16, b1 = (uint32_t)(yt[k].y >> 16) << 16;   // (b << 16) * r >> 32 == (b * r) >> 16
+        const uint2 u = *reinterpret_cast<const uint2*>(hbuf + r0 * (PYR_TW / 2) + 2 * gq);
+        const uint2 v = *reinterpret_cast<const uint2*>(hbuf + r1 * (PYR_TW / 2) + 2 * gq);
+        uint32_t o0 = (__umulhi(b0, u.x & 0xffffu) + __umulhi(b1, v.x & 0xffffu) + 2u) >> 2;
+        uint32_t o1 = (__umulhi(b0, u.x >> 16) + __umulhi(b1, v.x >> 16) + 2u) >> 2;
+        uint32_t o2 = (__umulhi(b0, u.y & 0xffffu) + __umulhi(b1, v.y & 0xffffu) + 2u) >> 2;
+        uint32_t o3 = (__umulhi(b0, u.y >> 16) + __umulhi(b1, v.y >> 16) + 2u) >> 2;
+        const int x = x0 + 4 * gq;
+        if (x >= a.dw) o0 = 0; if (x + 1 >= a.dw) o1 = 0; if (x + 2 >= a.dw) o2 = 0; if (x + 3 >= a.dw) o3 = 0;   // deterministic padding
+        uint8_t* D = a.dst + (size_t)img * a.dimg_bytes + (size_t)dy * a.dpitch + x;
+        *reinterpret_cast<uint32_t*>(D) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+    }
 }
 
 void launch_pyramid_level(sfe_context* c, int level, int nimg)
@@ -68,7 +93,7 @@ void launch_pyramid_level(sfe_context* c, int level, int nimg)
     PyrArgs a;
     a.dst = c->d_pyr + g.lvl_ofs; a.dpitch = g.pitch; a.dimg_bytes = g.img_bytes;
     a.dw = g.w; a.dh = g.h; a.sh = c->pack.g[level - 1].h;
-    a.xtab = c->d_xtab[level]; a.ytab = c->d_ytab[level];
+    a.gtab = c->d_gtab[level]; a.ytab = c->d_ytab[level];
     dim3 grid((g.w + PYR_TW - 1) / PYR_TW, (g.h + PYR_TH - 1) / PYR_TH, nimg);
     pyramid_kernel<<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
     c->launches++;

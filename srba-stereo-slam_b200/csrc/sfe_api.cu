@@ -189,6 +189,27 @@ static int create_impl(sfe_context* c)
             const int y1 = std::min(y0 + PYR_TH, P.g[l].h) - 1;
             if (c->ytab[l][y1].x + 2 - std::max(c->ytab[l][y0].x, 0) > PYR_BOX_H) { c->err = "pyramid tile footprint exceeds TMA box (y)"; return SFE_ERR_INVALID; }
         }
+        {   // gather plan of the horizontal pass, one entry per 4 destination columns
+            const int ng = (P.g[l].w + 3) / 4;
+            std::vector<uint32_t> gt((size_t)ng * 6);
+            for (int q = 0; q < ng; ++q) {
+                int sx[4]; uint32_t cf[4];
+                for (int e = 0; e < 4; ++e) {
+                    const int d = std::min(4 * q + e, P.g[l].w - 1);
+                    sx[e] = c->xtab[l][d].x; cf[e] = (uint32_t)c->xtab[l][d].y;
+                }
+                uint32_t sel = 0;
+                for (int e = 0; e < 4; ++e) {
+                    const int o = sx[e] - sx[0];
+                    if (o < 0 || o > 6) { c->err = "resize gather plan: offset out of PRMT range"; return SFE_ERR_INVALID; }
+                    sel |= (uint32_t)(o | ((o + 1) << 4)) << (8 * e);
+                }
+                gt[(size_t)q * 6 + 0] = (uint32_t)sx[0]; gt[(size_t)q * 6 + 1] = sel;
+                for (int e = 0; e < 4; ++e) gt[(size_t)q * 6 + 2 + e] = cf[e];
+            }
+            SFE_CUDA(c, dalloc(&c->d_gtab[l], gt.size()));
+            SFE_CUDA(c, cudaMemcpy(c->d_gtab[l], gt.data(), gt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
         SFE_CUDA(c, dalloc(&c->d_xtab[l], c->xtab[l].size()));
         SFE_CUDA(c, dalloc(&c->d_ytab[l], c->ytab[l].size()));
         SFE_CUDA(c, cudaMemcpy(c->d_xtab[l], c->xtab[l].data(), c->xtab[l].size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -212,6 +233,22 @@ static int create_impl(sfe_context* c)
         if (r) return r;
         r = make_image_map(c, enc, &c->pyrsrc_map[l], c->d_pyr + g.lvl_ofs, g.w, g.h, g.pitch, NI, PYR_BOX_W, PYR_BOX_H);
         if (r) return r;
+    }
+    {   // tile tables: blockIdx.x -> (level, tile origin), so the kernels need no search and no division
+        std::vector<int4> ft_tab, bt_tab;
+        for (int l = 0; l < L; ++l) {
+            const LevelGeom& g = P.g[l];
+            for (int ty = 0; ty < g.ftiles_y; ++ty) for (int tx = 0; tx < g.ftiles_x; ++tx)
+                ft_tab.push_back(make_int4(l, (g.rx0 & ~3) + tx * FAST_TW, g.ry0 + ty * FAST_TH, 0));
+            for (int ty = 0; ty < g.btiles_y; ++ty) for (int tx = 0; tx < g.btiles_x; ++tx)
+                bt_tab.push_back(make_int4(l, tx * BLUR_TW, ty * BLUR_TH, 0));
+        }
+        if (!ft_tab.empty()) {
+            SFE_CUDA(c, dalloc(&c->d_ftile_tab, ft_tab.size()));
+            SFE_CUDA(c, cudaMemcpy(c->d_ftile_tab, ft_tab.data(), ft_tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        }
+        SFE_CUDA(c, dalloc(&c->d_btile_tab, bt_tab.size()));
+        SFE_CUDA(c, cudaMemcpy(c->d_btile_tab, bt_tab.data(), bt_tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
     }
     // blur taps for the float mode: getGaussianKernel(7, 2, CV_32F)
     {
@@ -251,8 +288,8 @@ extern "C" void sfe_destroy(sfe_context* c)
     cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_raw); cudaFree(c->d_raw_count);
     cudaFree(c->d_sel_xy); cudaFree(c->d_sel_resp); cudaFree(c->d_sel_count); cudaFree(c->d_kp); cudaFree(c->d_desc);
     cudaFree(c->d_kp_count); cudaFree(c->d_matches); cudaFree(c->d_match_count); cudaFree(c->d_status);
-    cudaFree(c->d_packed); cudaFree(c->d_bf_q); cudaFree(c->d_bf_t); cudaFree(c->d_bf_best); cudaFree(c->d_bf_ofs);
-    for (int l = 0; l < SFE_MAX_LEVELS; ++l) { cudaFree(c->d_xtab[l]); cudaFree(c->d_ytab[l]); }
+    cudaFree(c->d_packed); cudaFree(c->d_ftile_tab); cudaFree(c->d_btile_tab); cudaFree(c->d_bf_q); cudaFree(c->d_bf_t); cudaFree(c->d_bf_best); cudaFree(c->d_bf_ofs);
+    for (int l = 0; l < SFE_MAX_LEVELS; ++l) { cudaFree(c->d_xtab[l]); cudaFree(c->d_ytab[l]); cudaFree(c->d_gtab[l]); }
     cudaFreeHost(c->h_images); cudaFreeHost(c->h_kp); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_matches);
     cudaFreeHost(c->h_kp_count); cudaFreeHost(c->h_match_count); cudaFreeHost(c->h_status); cudaFreeHost(c->h_counts);
     if (c->ev_start) cudaEventDestroy(c->ev_start);

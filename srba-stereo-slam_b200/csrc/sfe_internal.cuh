@@ -110,6 +110,9 @@ struct sfe_context {
     std::vector<std::vector<int2>> xtab, ytab;   // host resize tables (kept for debugging)
     int2* d_xtab[SFE_MAX_LEVELS] = {};       // per destination level: {src offset, a0 | a1<<16}
     int2* d_ytab[SFE_MAX_LEVELS] = {};
+    uint32_t* d_gtab[SFE_MAX_LEVELS] = {};
+    int4* d_ftile_tab = nullptr;             // FAST tile -> {level, tx0, ty0, 0}
+    int4* d_btile_tab = nullptr;             // blur tile -> {level, x0, y0, 0}   // per 4 destination columns: {src base, PRMT selectors, 4 coefficient pairs}
     CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 176x24-box maps over the same levels, source side of the pyramid kernel
     int NI = 0;                              // images the arenas are sized for (2*max_pairs)
     int sel_cand_cap = 0;                    // select kernel: shared candidate list capacity
