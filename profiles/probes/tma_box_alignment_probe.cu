@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <vector>
-#include "../srba-stereo-slam_b200/csrc/sfe_internal.cuh"
+#include "../../srba-stereo-slam_b200/csrc/sfe_internal.cuh"
 __global__ void k(const __grid_constant__ CUtensorMap m, int x, int y, int z, uint8_t* out, int bw, int bh)
 {
     extern __shared__ __align__(128) uint8_t tile[];

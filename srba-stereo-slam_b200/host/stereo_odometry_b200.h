@@ -1,0 +1,131 @@
+// stereo_odometry_b200.h -- drop-in for the members of rso::CStereoOdometryEstimator (famoreno/stereo-vo,
+// `libstereo-odometry.h`, not vendored by the reference) that famoreno/srba-stereo-slam touches.  Every member is
+// listed with the reference call site that relies on it; the detect / describe / match work is
+// done by the CUDA library behind include/srba_b200.h, there is no CPU path.
+//
+// What is NOT here: the robust least-squares pose solver (processNewImagePair's outPose, getChangeInPose --
+// reference EST.cpp:327, 2139-2146).  BASELINE.json keeps the SRBA/LM side on the host and out of scope;
+// getChangeInPose is declared for link compatibility and reports "not provided".
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+#include "cv_compat.h"
+#include "../../include/srba_b200.h"
+
+namespace rso {
+
+// Stand-in for mrpt::obs::CObservationStereoImagesPtr when MRPT is absent: two rectified 8-bit grey images.
+struct CObservationStereoImages {
+    const uint8_t* imageLeft = nullptr; const uint8_t* imageRight = nullptr;
+    int width = 0, height = 0; size_t stride = 0;
+};
+typedef std::shared_ptr<CObservationStereoImages> CObservationStereoImagesPtr;
+
+struct TStereoCameraLite { int ncols = 1241, nrows = 376; double fx = 707.0912, fy = 707.0912, cx = 601.8873, cy = 183.1104, baseline = 0.54; };
+
+class CStereoOdometryEstimator {
+public:
+    // ---- parameter blocks (enumerations as documented in the reference's config comments, example.ini:9,33,51) ----
+    struct TDetectParams {
+        enum TDetectMethod { dmORB = 0, dmFAST_ORB, dmFASTER, dmKLT };
+        TDetectMethod detect_method = dmORB;          // forced at EST.cpp:1135
+        int initial_FAST_threshold = 20;              // EST.cpp:1140
+        int fast_min_th = 5, fast_max_th = 30;        // example.ini:15-16
+        int orb_nlevels = 8;                          // EST.cpp:1141 (reference default: 1, UTL.h:288)
+        int orb_nfeats = 500;                         // EST.cpp:1142
+    };
+    struct TLeftRightMatchParams {
+        enum TLRMatchMethod { smDescBF = 0, smDescRbR, smSAD };
+        TLRMatchMethod match_method = smDescRbR;      // forced at EST.cpp:1136
+        double max_y_diff = 2.0;                      // kitti.ini:17
+        bool enable_robust_1to1_match = false;        // kitti.ini:18
+        bool rectified_images = true;                 // kitti.ini:19
+        double orb_max_distance = 60;                 // kitti.ini:24
+        int orb_min_th = 30, orb_max_th = 100;        // example.ini:45-46
+        double min_disparity = 0.0, max_disparity = 1e9;
+    };
+    struct TInterFrameMatchingParams {
+        enum TIFMMethod { ifmDescBF = 0, ifmDescWin, ifmSAD, ifmOpticalFlow };
+        TIFMMethod ifm_method = ifmDescBF;            // forced at EST.cpp:1137
+        double orb_max_distance = 60;                 // "the same values as for stereo-matching are employed", kitti.ini:38
+    };
+    struct TLeastSquaresParams { bool use_custom_initial_pose = false; };   // toggled at EST.cpp:2138,2147
+
+    struct TStereoOdometryRequest {
+        CObservationStereoImagesPtr stereo_imgs;      // EST.cpp:111,258
+        bool use_precomputed_data = false;            // EST.cpp:259
+        bool repeat = false;                          // EST.cpp:260,278,285,315
+        TStereoCameraLite stereo_cam;                 // EST.cpp:1167
+    };
+    struct TStereoOdometryResult {
+        double outPose[6] = { 0, 0, 0, 0, 0, 0 };     // host least-squares solver: not computed here
+        bool valid = false;                           // EST.cpp:318
+        std::vector<std::pair<size_t, size_t>> detected_feats;   // [octave] (left, right), EST.cpp:268
+        std::vector<size_t> stereo_matches;           // [octave], EST.cpp:269,273,288,297
+        size_t tracked_feats_from_last_frame = 0;     // EST.cpp:359
+        size_t tracked_feats_from_last_KF = 0;        // EST.cpp:360,378
+        int num_it = 0, num_it_final = 0;
+        std::vector<double> out_residual;
+    };
+
+    TDetectParams params_detect;
+    TLeftRightMatchParams params_lr_match;
+    TInterFrameMatchingParams params_if_match;
+    TLeastSquaresParams params_least_squares;
+
+    CStereoOdometryEstimator();
+    ~CStereoOdometryEstimator();
+    CStereoOdometryEstimator(const CStereoOdometryEstimator&) = delete;
+    CStereoOdometryEstimator& operator=(const CStereoOdometryEstimator&) = delete;
+
+    // EST.cpp:1122-1131: sections RECTIFY, DETECT, MATCH, IF-MATCH, LEAST_SQUARES, GUI, GENERAL of a plain .ini file.
+    void loadParamsFromConfigFile(const std::string& ini_file, const std::vector<std::string>& sections);
+    void setVerbosityLevel(int v) { m_verbose = v; }                       // EST.cpp:1132
+    void dumpToConsole() const;                                           // EST.cpp:1144
+
+    // EST.cpp:112,267.  Creates the GPU context on first use from params_* and the image size.  Returns result.valid.
+    bool processNewImagePair(TStereoOdometryRequest& request, TStereoOdometryResult& result);
+
+    void setThisFrameAsKF();                                              // EST.cpp:113
+    void resetIds();                                                      // EST.cpp:403,620
+
+    int  getFASTThreshold() const { return m_fast_th; }                   // EST.cpp:275
+    void setFASTThreshold(int th);                                        // EST.cpp:277,302,310
+    bool isFASTThMin() const { return m_fast_th <= params_detect.fast_min_th; }   // EST.cpp:275,301
+    int  getORBThreshold() const { return m_orb_th; }                     // EST.cpp:281
+    void setORBThreshold(int th);                                         // EST.cpp:284,304,311
+    bool isORBThMax() const { return m_orb_th >= params_lr_match.orb_max_th; }    // EST.cpp:281
+    void resetORBThreshold() { setORBThreshold((int)params_lr_match.orb_max_distance); }   // EST.cpp:303
+
+    // CStereoSLAMKF.h:68-70: argument order and types of the reference.
+    void getValues(std::vector<cv::KeyPoint>& kpL, std::vector<cv::KeyPoint>& kpR, cv::Mat& descL, cv::Mat& descR,
+                   std::vector<cv::DMatch>& matches, std::vector<size_t>& matches_ID);
+
+    // EST.cpp:2139-2146: host least-squares solver, out of scope; always returns false and sets result.valid = false.
+    bool getChangeInPose(const std::vector<std::pair<size_t, size_t>>& tracked_pairs, const std::vector<cv::DMatch>& pre_matches,
+                         const std::vector<cv::DMatch>& cur_matches, const std::vector<cv::KeyPoint>& pre_left,
+                         const std::vector<cv::KeyPoint>& pre_right, const std::vector<cv::KeyPoint>& cur_left,
+                         const std::vector<cv::KeyPoint>& cur_right, const TStereoCameraLite& cam, TStereoOdometryResult& result,
+                         const std::vector<double>& initial);
+
+    sfe_context* context() { return m_ctx; }          // for CBoWManager / keyframe matching on the same GPU
+    const std::string& lastError() const { return m_err; }
+
+private:
+    bool ensureContext(int width, int height);
+    sfe_context* m_ctx = nullptr;
+    int m_w = 0, m_h = 0, m_fast_th = 20, m_orb_th = 60, m_verbose = 0;
+    std::string m_err;
+    // current frame (host copies of the GPU results)
+    std::vector<cv::KeyPoint> m_kpL, m_kpR; cv::Mat m_descL, m_descR; std::vector<cv::DMatch> m_matches; std::vector<size_t> m_ids;
+    // previous frame, for ifmDescBF id propagation
+    cv::Mat m_prev_matched_desc; std::vector<size_t> m_prev_ids;
+    std::vector<size_t> m_kf_ids;                     // ids alive at the last keyframe / resetIds()
+    size_t m_next_id = 0; bool m_have_frame = false;
+};
+
+}  // namespace rso

@@ -1,0 +1,88 @@
+"""GPU (-m gpu): the C++ adapter classes (same names/signatures as the reference: rso::CStereoOdometryEstimator,
+CStereoSLAMKF, CBoWManager + the BFMatcher part of m_internal_data_association) driven like performStereoSLAM
+drives them (EST.cpp:82-216, 413-447), checked against the oracle."""
+import os
+import struct
+import subprocess
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "srba-stereo-slam_b200", "host")
+
+
+def _write_voc_yml(voc, path):
+    """Re-serialise the flattened vocabulary fixture in DBoW2's YAML layout so the C++ loader is exercised too."""
+    with open(path, "w") as f:
+        f.write("%%YAML:1.0\nvocabulary:\n   k: %d\n   L: %d\n   scoringType: 0\n   weightingType: 0\n   nodes:\n" % (voc["k"], voc["L"]))
+        parent = voc["parent"]
+        order = []                                      # file order must list a node's children in child_idx order
+        for p in range(voc["nnodes"]):
+            order.extend(voc["child_idx"][voc["child_ofs"][p]:voc["child_ofs"][p + 1]].tolist())
+        for nid in order:
+            bits = np.unpackbits(voc["node_desc"][nid], bitorder="little")[::-1]       # char c <-> bit 255-c
+            f.write('      - { nodeId:%d, parentId:%d, weight:%s,\n          descriptor:"%s" }\n' %
+                    (nid, parent[nid], repr(float(voc["node_weight"][nid])), "".join(map(str, bits))))
+        f.write("   words:\n")
+        for nid in np.nonzero(voc["node_word"] >= 0)[0]:
+            f.write("      - { wordId:%d, nodeId:%d }\n" % (voc["node_word"][nid], nid))
+
+
+def test_adapters_follow_the_reference_call_sequence(tmp_path, voc):
+    from srba_stereo_slam_b200 import frontend, synth
+    from oracle import oracle as orc
+    W, H, NF, NL, NFEAT = 640, 192, 3, 4, 300
+    frames = synth.CorridorScene(seed=6, width=W, height=H).sequence(NF)
+    fb = tmp_path / "frames.bin"; frames.tofile(fb)
+    vy = tmp_path / "voc.yml"; _write_voc_yml(voc, vy)
+    ob = tmp_path / "out.bin"
+    r = subprocess.run([os.path.join(HOST, "host_test"), str(fb), str(W), str(H), str(NF), str(NL), str(NFEAT), str(vy), str(ob)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(ob, "rb").read(); off = 0
+    KD, MD = frontend.KEYPOINT_DTYPE, frontend.DMATCH_DTYPE
+    prev = None; odb = []; next_id = 0
+    for k in range(NF):
+        nl, nr, nm, tracked, nq, nda = struct.unpack_from("6i", data, off); off += 24
+        kl = np.frombuffer(data, KD, nl, off); off += 28 * nl
+        kr = np.frombuffer(data, KD, nr, off); off += 28 * nr
+        dl = np.frombuffer(data, np.uint8, nl * 32, off).reshape(nl, 32); off += 32 * nl
+        dr = np.frombuffer(data, np.uint8, nr * 32, off).reshape(nr, 32); off += 32 * nr
+        m = np.frombuffer(data, MD, nm, off); off += 16 * nm
+        ids = np.frombuffer(data, np.int64, nm, off); off += 8 * nm
+        qr = [struct.unpack_from("=id", data, off + 12 * i) for i in range(nq)]; off += 12 * nq
+        da = np.frombuffer(data, MD, nda, off); off += 16 * nda
+        # --- oracle
+        ol, odl, _ = orc.orb_extract(frames[k, 0], nfeatures=NFEAT, nlevels=NL)
+        orr, odr, _ = orc.orb_extract(frames[k, 1], nfeatures=NFEAT, nlevels=NL)
+        om = orc.match_rowband(ol, odl, orr, odr)
+        for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(kl[f], ol[f]) and np.array_equal(kr[f], orr[f]), (k, f)
+        assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+        assert np.array_equal(m["queryIdx"], om["queryIdx"]) and np.array_equal(m["trainIdx"], om["trainIdx"]) and nm > 30
+        cur = odl[om["queryIdx"]]
+        # id propagation (ifmDescBF): best previous match under the ORB threshold, each previous id claimed once
+        exp_ids = np.zeros(nm, np.int64); exp_tracked = 0
+        if prev is not None:
+            bf = orc.match_bf(cur, prev[0]); claimed = set()
+            for i in range(nm):
+                t = int(bf["trainIdx"][i])
+                if bf["distance"][i] <= 60 and t not in claimed:
+                    exp_ids[i] = prev[1][t]; claimed.add(t); exp_tracked += 1
+                else:
+                    exp_ids[i] = next_id; next_id += 1
+            oda = orc.match_bf(cur, prev[0])                       # KF-to-KF brute force on the matched subsets (EST.cpp:1432-1452)
+            assert np.array_equal(da["trainIdx"], oda["trainIdx"]) and np.array_equal(da["distance"], oda["distance"])
+            assert np.array_equal(da["queryIdx"], np.arange(nm))
+        else:
+            exp_ids = np.arange(nm, dtype=np.int64); next_id = nm
+        assert np.array_equal(ids, exp_ids) and tracked == exp_tracked
+        if k > 0:
+            assert tracked > 10
+            ores = orc.bow_query(voc, odb, odl, 4)
+            assert [q[0] for q in qr] == [o[0] for o in ores] and [q[1] for q in qr] == [o[1] for o in ores]
+        w_, wt_ = orc.bow_transform(voc, odl)
+        odb.append(orc.bow_vector(voc, w_, wt_))
+        prev = (cur, exp_ids)
+    assert off == len(data)
