@@ -139,13 +139,13 @@ static const int RING_DY[16] = { 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1
 
 static int fast_arc_strength(const uint8_t* p, int stride)
 {
-    int d[16], best = 0;
+    int d[32], best = 0;
     int v = p[0];
-    for (int k = 0; k < 16; ++k) d[k] = v - p[RING_DY[k] * stride + RING_DX[k]];
+    for (int k = 0; k < 16; ++k) d[k] = d[k + 16] = v - p[RING_DY[k] * stride + RING_DX[k]];
     for (int k = 0; k < 16; ++k) {
-        int mn = 1 << 30, mx = -(1 << 30);
-        for (int j = 0; j < 9; ++j) {
-            int e = d[(k + j) & 15];
+        int mn = d[k], mx = d[k];
+        for (int j = 1; j < 9; ++j) {
+            int e = d[k + j];
             if (e < mn) mn = e;
             if (e > mx) mx = e;
         }
@@ -155,15 +155,24 @@ static int fast_arc_strength(const uint8_t* p, int stride)
     return best;
 }
 
-/* dense score map: 0 = not a corner, else score (>= th) */
+/* dense score map: 0 = not a corner, else score (>= th).  The opposite-pair test only skips pixels that cannot
+ * be corners (every 9-arc contains one pixel of each opposite pair); it does not change the result. */
 void orc_fast_score_map(const uint8_t* img, int w, int h, int stride, int th, uint8_t* score /* w*h */)
 {
     memset(score, 0, (size_t)w * h);
-    for (int y = 3; y < h - 3; ++y)
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t* row = img + (size_t)y * stride;
         for (int x = 3; x < w - 3; ++x) {
-            int s = fast_arc_strength(img + (size_t)y * stride + x, stride);
+            const uint8_t* p = row + x;
+            int v = p[0], lo = v - th, hi = v + th;
+            int p0 = p[3 * stride], p8 = p[-3 * stride], p4 = p[3], p12 = p[-3];
+            int br = (p0 > hi || p8 > hi) && (p4 > hi || p12 > hi);
+            int dk = (p0 < lo || p8 < lo) && (p4 < lo || p12 < lo);
+            if (!(br || dk)) continue;
+            int s = fast_arc_strength(p, stride);
             if (s > th) score[(size_t)y * w + x] = (uint8_t)(s - 1);
         }
+    }
 }
 
 /* returns the number of keypoints; xy/sc may be NULL to count only. */
@@ -312,20 +321,29 @@ void orc_gauss7_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* 
     int32_t t[7];
     orc_gauss7_taps(t);
     int32_t* rows = malloc(sizeof(int32_t) * (size_t)w * h);
-    for (int y = 0; y < h; ++y)
+    int* xi = malloc(sizeof(int) * (w + 6));        /* reflect-101 column / row index tables */
+    int* yi = malloc(sizeof(int) * (h + 6));
+    for (int x = -3; x < w + 3; ++x) xi[x + 3] = reflect101(x, w);
+    for (int y = -3; y < h + 3; ++y) yi[y + 3] = reflect101(y, h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* r = src + (size_t)y * sstride;
+        int32_t* o = rows + (size_t)y * w;
         for (int x = 0; x < w; ++x) {
-            int s = 0;
-            for (int k = -3; k <= 3; ++k) s += t[k + 3] * src[(size_t)y * sstride + reflect101(x + k, w)];
-            rows[(size_t)y * w + x] = s;
+            const int* c = xi + x;
+            o[x] = t[0] * r[c[0]] + t[1] * r[c[1]] + t[2] * r[c[2]] + t[3] * r[c[3]] + t[4] * r[c[4]] + t[5] * r[c[5]] + t[6] * r[c[6]];
         }
-    for (int y = 0; y < h; ++y)
+    }
+    for (int y = 0; y < h; ++y) {
+        const int32_t* r[7];
+        for (int k = 0; k < 7; ++k) r[k] = rows + (size_t)yi[y + k] * w;
+        uint8_t* o = dst + (size_t)y * dstride;
         for (int x = 0; x < w; ++x) {
-            int s = 0;
-            for (int k = -3; k <= 3; ++k) s += t[k + 3] * rows[(size_t)reflect101(y + k, h) * w + x];
+            int s = t[0] * r[0][x] + t[1] * r[1][x] + t[2] * r[2][x] + t[3] * r[3][x] + t[4] * r[4][x] + t[5] * r[5][x] + t[6] * r[6][x];
             s = (s + (1 << 15)) >> 16;
-            dst[(size_t)y * dstride + x] = (uint8_t)(s > 255 ? 255 : s);
+            o[x] = (uint8_t)(s > 255 ? 255 : s);
         }
-    free(rows);
+    }
+    free(rows); free(xi); free(yi);
 }
 
 /* Alternative blur arithmetic (blur_mode 1): what cv::sepFilter2D does since OpenCV 3.4/4.x when
@@ -452,11 +470,11 @@ int orc_orb_extract(const uint8_t* img, int W, int H, int stride, const orc_orb_
         int level_n = 0;
         int e = prm->edge_threshold;
         if (w > 2 * e && h > 2 * e && w >= 7 && h >= 7) {
-            int cap_raw = orc_fast9_nms(cur, w, h, w, prm->fast_threshold, NULL, NULL, NULL, 0);
+            int cap_raw = ((w + 1) / 2) * ((h + 1) / 2);    /* NMS: no two 8-adjacent maxima */
             int32_t* xs = malloc(sizeof(int32_t) * (cap_raw + 1));
             int32_t* ys = malloc(sizeof(int32_t) * (cap_raw + 1));
             int32_t* sc = malloc(sizeof(int32_t) * (cap_raw + 1));
-            orc_fast9_nms(cur, w, h, w, prm->fast_threshold, xs, ys, sc, cap_raw);
+            cap_raw = orc_fast9_nms(cur, w, h, w, prm->fast_threshold, xs, ys, sc, cap_raw);
             /* runByImageBorder(edgeThreshold) */
             int m = 0;
             for (int i = 0; i < cap_raw; ++i)
