@@ -200,6 +200,25 @@ int sfe_bow_db_size(const sfe_bow* bow);
 /* Device-resident batched transform (descriptors already in HBM), asynchronous. */
 int sfe_bow_transform_device(sfe_bow* bow, const uint8_t* d_desc, int n, int32_t* d_word, double* d_weight);
 
+/* ---- full front-end batch: BoW + keyframe store + data association ----------------------------------
+ * Replaces, per candidate keyframe (EST.cpp): queryDB(new_kf, qResults, 4) (:424-427), the similar-KF list =
+ * previous keyframe + BoW hits (:435, :1758), the matched-subset gathers (:1351-1359, :1432-1440),
+ * BFMatcher.match against each (:1447-1452) and insertIntoDB (:919) -- batched, device-resident.
+ * Every pair of the last processed stereo batch is appended as a keyframe; frame g only sees entries < g.
+ * Results per frame: <= 4 query hits (ids are store indices, best first), 5 association slots
+ * {previous keyframe, hit 0..3} with the keyframe index (-1 = empty / duplicate of the previous keyframe) and,
+ * per slot, one packed (dist<<16 | train index) per stereo-matched feature (indices into the other
+ * keyframe's match list, as in t_kf_da_info, srba-stereo-slam_utils.h:55-66). */
+typedef struct sfe_kfdb sfe_kfdb;
+int  sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_frames, sfe_kfdb** out);
+void sfe_kfdb_destroy(sfe_kfdb* db);
+int  sfe_kfdb_size(const sfe_kfdb* db);
+int  sfe_kfdb_reset(sfe_kfdb* db);
+int  sfe_kfdb_process_batch(sfe_kfdb* db, int npairs);     /* asynchronous on sfe_stream() */
+int  sfe_kfdb_results(sfe_kfdb* db, const int32_t** query_ids /* [n][4] */, const double** query_scores /* [n][4] */,
+                      const int32_t** query_n /* [n] */, const int32_t** pair_kf /* [n][5] */,
+                      const uint32_t** best /* [n][5][capacity] */, const int32_t** matched_n /* [n] */);
+
 #ifdef __cplusplus
 }
 #endif

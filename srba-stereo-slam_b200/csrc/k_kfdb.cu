@@ -1,0 +1,397 @@
+// k_kfdb.cu -- the "full front-end" batch: for every stereo pair of a processed batch, BoW transform + database
+// query + database add of the left descriptors, gather of the stereo-matched left descriptors into a
+// device-resident keyframe store, and brute-force Hamming match against the previous keyframe and the BoW hits.
+//
+// Reference sequence per candidate keyframe (src/CSRBAStereoSLAMEstimator.cpp): getDataFromVOEngine (:413-418),
+// m_bow_manager.queryDB(new_kf, qResults, 4) (:424-427), m_get_similar_kfs = previous KF + BoW hits (:435, :1758),
+// m_data_association -> gather matched-subset descriptors (:1351-1359, :1432-1440) + BFMatcher.match (:1447-1452),
+// m_bow_manager.insertIntoDB (:919).  Here every frame of the batch is treated as a keyframe (throughput mode,
+// BASELINE.json configs[2]); frame g only sees database entries < g, exactly as if the frames had been
+// processed one by one (DBoW2's query has the same max_id notion).
+//
+// BoW scoring is exact DBoW2 L1 in FP64, accumulated per entry in ascending word order (bit-identical to the
+// single-keyframe path and the CPU oracle): one warp per database entry tests its sorted words against 16 query
+// bitmaps held in shared memory (hits are ~2 % of the tests), hits are replayed in word order by the lane that
+// owns the query.  Integer/popc work elsewhere; tensor cores unused by design.
+#include "bow_internal.cuh"
+#include <algorithm>
+#include <cstring>
+
+#define KF_QT 16                 // queries per score CTA (bitmaps in shared memory)
+#define KF_PAIRS 5               // previous keyframe + 4 BoW hits (EST.cpp:426, :1758)
+
+struct BfPair { int q_start, nq, t_start, nt, out_start; };
+
+struct sfe_kfdb {
+    sfe_context* ctx = nullptr; sfe_bow* bow = nullptr;
+    int cap_frames = 0, stride = 0, B = 0, n_frames = 0, nwords = 0, bm_words = 0;
+    uint8_t* d_msub = nullptr; int32_t* d_msub_n = nullptr;
+    int32_t* d_dbw = nullptr; double* d_dbv = nullptr; int32_t* d_dbn = nullptr;
+    int32_t* d_word = nullptr; double* d_weight = nullptr;
+    uint32_t* d_bitmap = nullptr; double* d_dense = nullptr;
+    double* d_score = nullptr; int32_t* d_common = nullptr;
+    int32_t* d_qid = nullptr; double* d_qscore = nullptr; int32_t* d_qn = nullptr;
+    BfPair* d_pairs = nullptr; int32_t* d_pair_kf = nullptr; uint32_t* d_best = nullptr;
+    int32_t* h_qid = nullptr; double* h_qscore = nullptr; int32_t* h_qn = nullptr; int32_t* h_pair_kf = nullptr; uint32_t* h_best = nullptr;
+    int32_t* h_msub_n = nullptr;
+    int last_base = 0, last_n = 0;
+};
+
+#define KF_CUDA(d, call) SFE_CUDA((d)->ctx, call)
+
+__device__ __forceinline__ int kf_ham256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1)
+{
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---- 1. gather the stereo-matched left descriptors of each pair into the keyframe store ----------------------
+__global__ void kf_gather_kernel(const uint8_t* __restrict__ desc, const sfe_dmatch* __restrict__ matches,
+                                 const int32_t* __restrict__ match_count, int cap, int base,
+                                 uint8_t* __restrict__ msub, int32_t* __restrict__ msub_n)
+{
+    const int p = blockIdx.y;
+    const int n = min(match_count[p], cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) msub_n[base + p] = n;
+    const int k = blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    if (k >= n) return;
+    const int qi = matches[(size_t)p * cap + k].queryIdx;
+    const uint4* src = reinterpret_cast<const uint4*>(desc + ((size_t)(2 * p) * cap + qi) * 32);
+    reinterpret_cast<uint4*>(msub + ((size_t)(base + p) * cap + k) * 32)[half] = __ldg(src + half);
+}
+
+// ---- 2. vocabulary transform of every left descriptor of the batch (8 lanes per descriptor) --------------------
+__global__ void __launch_bounds__(256)
+kf_transform_kernel(const int32_t* __restrict__ first, const int32_t* __restrict__ nchild, const uint4* __restrict__ ndesc,
+                    const int32_t* __restrict__ nword, const double* __restrict__ nweight, int depth,
+                    const uint8_t* __restrict__ desc, const int32_t* __restrict__ kp_count, int cap,
+                    int32_t* __restrict__ word, double* __restrict__ weight)
+{
+    const int p = blockIdx.y;
+    const int n = min(kp_count[2 * p], cap);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gtid >> 3, c = gtid & 7;
+    if ((blockIdx.x * blockDim.x >> 3) >= n) return;
+    const int ii = min(i, n - 1);
+    const uint4* q = reinterpret_cast<const uint4*>(desc + ((size_t)(2 * p) * cap + ii) * 32);
+    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+    int node = 0;
+    for (int d = 0; d < depth; ++d) {
+        const int nc = __ldg(nchild + node), fc = __ldg(first + node);
+        uint32_t key = 0xffffffffu;
+        if (c < nc) {
+            const uint4* pp = ndesc + 2 * (size_t)(fc + c);
+            key = ((uint32_t)kf_ham256(q0, q1, __ldg(pp), __ldg(pp + 1)) << 4) | (uint32_t)c;
+        }
+        key = min(key, __shfl_xor_sync(0xffffffffu, key, 1));
+        key = min(key, __shfl_xor_sync(0xffffffffu, key, 2));
+        key = min(key, __shfl_xor_sync(0xffffffffu, key, 4));
+        if (nc > 0) node = fc + (int)(key & 15u);
+    }
+    if (c == 0 && i < n) { word[(size_t)p * cap + i] = __ldg(nword + node); weight[(size_t)p * cap + i] = __ldg(nweight + node); }
+}
+
+// ---- 3. BoW vector of each pair, written straight into its (fixed-stride) database slot -------------------------
+#define KV_THREADS 1024
+__global__ void __launch_bounds__(KV_THREADS)
+kf_vector_kernel(const int32_t* __restrict__ word, const double* __restrict__ weight, const int32_t* __restrict__ kp_count,
+                 int cap, int npow2, int base, int32_t* __restrict__ dbw, double* __restrict__ dbv, int32_t* __restrict__ dbn)
+{
+    extern __shared__ uint32_t keys[];
+    __shared__ int s_m;
+    __shared__ double s_norm;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int n = min(kp_count[2 * p], cap);
+    const int32_t* w_in = word + (size_t)p * cap; const double* wt_in = weight + (size_t)p * cap;
+    int32_t* out_w = dbw + (size_t)(base + p) * cap; double* out_v = dbv + (size_t)(base + p) * cap;
+    for (int i = tid; i < npow2; i += KV_THREADS)
+        keys[i] = (i < n && wt_in[i] > 0.0) ? (((uint32_t)w_in[i] << 16) | (uint32_t)i) : 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npow2; i += KV_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (int i = tid; i < npow2; i += KV_THREADS) {
+        const uint32_t k = keys[i];
+        if (k == 0xffffffffu) continue;
+        const uint32_t w = k >> 16;
+        if (i > 0 && (keys[i - 1] >> 16) == w) continue;
+        double s = 0.0;
+        for (int j = i; j < npow2 && keys[j] != 0xffffffffu && (keys[j] >> 16) == w; ++j) s += wt_in[keys[j] & 0xffffu];
+        int rank = 0;
+        for (int j = 1; j <= i; ++j) rank += (keys[j] >> 16) != (keys[j - 1] >> 16);
+        out_w[rank] = (int32_t)w; out_v[rank] = s;
+        atomicAdd(&s_m, 1);
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (tid == 0) {
+        double norm = 0.0;
+        for (int i = 0; i < m; ++i) norm += fabs(out_v[i]);
+        s_norm = norm; dbn[base + p] = m;
+    }
+    __syncthreads();
+    const double norm = s_norm;
+    if (norm > 0.0) for (int i = tid; i < m; i += KV_THREADS) out_v[i] = out_v[i] / norm;
+}
+
+// ---- 4. query side: bitmap + dense vector of each pair's BoW vector (and the inverse, to clean up) -------------
+__global__ void kf_query_prep_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn,
+                                     int cap, int base, int nwords, int bm_words, uint32_t* __restrict__ bitmap,
+                                     double* __restrict__ dense, int clear)
+{
+    const int p = blockIdx.y, e = base + p;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dbn[e]) return;
+    const int w = dbw[(size_t)e * cap + i];
+    if (clear) { dense[(size_t)p * nwords + w] = 0.0; bitmap[(size_t)p * bm_words + (w >> 5)] = 0u; }
+    else { dense[(size_t)p * nwords + w] = dbv[(size_t)e * cap + i]; atomicOr(&bitmap[(size_t)p * bm_words + (w >> 5)], 1u << (w & 31)); }
+}
+
+// ---- 5. exact L1 scores: warp per database entry x 16 queries ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn, int cap,
+                int base, int nq, int nwords, int bm_words, const uint32_t* __restrict__ bitmap, const double* __restrict__ dense,
+                int score_stride, double* __restrict__ score, int32_t* __restrict__ common)
+{
+    extern __shared__ uint32_t bm[];                       // [KF_QT][bm_words]
+    const int q0 = blockIdx.y * KF_QT;
+    const int nqt = min(KF_QT, nq - q0);
+    for (int i = threadIdx.x; i < KF_QT * bm_words; i += blockDim.x) {
+        const int q = i / bm_words;
+        bm[i] = q < nqt ? bitmap[(size_t)(q0 + q) * bm_words + (i - q * bm_words)] : 0u;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // queries of this tile see entries < base + q; the newest query of the tile bounds the useful entries
+    if (e >= base + q0 + nqt - 1) return;
+    const int n = dbn[e];
+    const int32_t* ew = dbw + (size_t)e * cap; const double* ev = dbv + (size_t)e * cap;
+    double s = 0.0; int any = 0;                            // lane q (< KF_QT) accumulates query q0+q
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int i = c0 + lane;
+        const int w = i < n ? __ldg(ew + i) : 0;
+        const double dv = i < n ? __ldg(ev + i) : 0.0;
+        uint32_t mine = 0;                                  // lane q keeps the hit mask of query q for this chunk
+#pragma unroll
+        for (int q = 0; q < KF_QT; ++q) {
+            const bool hit = i < n && ((bm[q * bm_words + (w >> 5)] >> (w & 31)) & 1u);
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == q) mine = bal;
+        }
+        while (__any_sync(0xffffffffu, mine != 0u)) {       // replay hits in ascending word order
+            const int src = mine ? __ffs(mine) - 1 : 0;
+            const int ws = __shfl_sync(0xffffffffu, w, src);
+            const double ds = __shfl_sync(0xffffffffu, dv, src);
+            if (mine) {
+                const double qv = dense[(size_t)(q0 + lane) * nwords + ws];
+                s += fabs(qv - ds) - fabs(qv) - fabs(ds);
+                any = 1; mine &= mine - 1;
+            }
+        }
+    }
+    if (lane < nqt) {
+        const int q = q0 + lane;
+        const bool visible = e < base + q;                 // a frame only sees older entries
+        score[(size_t)q * score_stride + e] = s;
+        common[(size_t)q * score_stride + e] = (any && visible) ? 1 : 0;
+    }
+}
+
+// ---- 6. top-k per query (best first, ties -> lower id), k <= 4 ----------------------------------------------------
+__global__ void __launch_bounds__(256)
+kf_topk_kernel(const double* __restrict__ score, int32_t* __restrict__ common, int base, int score_stride, int k,
+               int32_t* __restrict__ qid, double* __restrict__ qscore, int32_t* __restrict__ qn)
+{
+    __shared__ double sv[8]; __shared__ int si[8];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ne = base + q;
+    const double* sc = score + (size_t)q * score_stride; int32_t* cm = common + (size_t)q * score_stride;
+    int found = 0;
+    for (int r = 0; r < k; ++r) {
+        double bv = 1e300; int bi = 0x7fffffff;
+        for (int e = tid; e < ne; e += 256)
+            if (cm[e] && (sc[e] < bv || (sc[e] == bv && e < bi))) { bv = sc[e]; bi = e; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w) if (sv[w] < sv[0] || (sv[w] == sv[0] && si[w] < si[0])) { sv[0] = sv[w]; si[0] = si[w]; }
+        }
+        __syncthreads();
+        bi = si[0]; bv = sv[0];
+        if (bi == 0x7fffffff) break;
+        if (tid == 0) { qid[q * 4 + found] = bi; qscore[q * 4 + found] = -bv / 2.0; cm[bi] = 0; }
+        ++found;
+        __syncthreads();
+    }
+    if (tid == 0) { qn[q] = found; for (int j = found; j < 4; ++j) { qid[q * 4 + j] = -1; qscore[q * 4 + j] = 0.0; } }
+}
+
+// ---- 7. pair list: previous keyframe + BoW hits (without duplicates of the previous keyframe) ---------------------
+__global__ void kf_pairs_kernel(const int32_t* __restrict__ qid, const int32_t* __restrict__ qn, const int32_t* __restrict__ msub_n,
+                                int base, int nq, int cap, BfPair* __restrict__ pairs, int32_t* __restrict__ pair_kf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * KF_PAIRS) return;
+    const int q = i / KF_PAIRS, slot = i - q * KF_PAIRS, g = base + q;
+    int kf = -1;
+    if (slot == 0) kf = g - 1;                                                         // may be -1 for the very first frame
+    else if (slot - 1 < qn[q]) { kf = qid[q * 4 + slot - 1]; if (kf == g - 1) kf = -1; }
+    BfPair pr;
+    pr.q_start = g * cap; pr.nq = kf >= 0 ? msub_n[g] : 0;
+    pr.t_start = max(kf, 0) * cap; pr.nt = kf >= 0 ? msub_n[kf] : 0;
+    pr.out_start = i * cap;
+    pairs[i] = pr; pair_kf[i] = kf;
+}
+
+// ---- 8. brute-force Hamming over the pair list ----------------------------------------------------------------------
+#define KBF_THREADS 128
+#define KBF_CHUNK 128
+#define KBF_SPLITS 4
+__global__ void __launch_bounds__(KBF_THREADS)
+kf_bf_kernel(const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs, uint32_t* __restrict__ best)
+{
+    __shared__ uint4 ts[KBF_CHUNK * 2];
+    const BfPair pr = pairs[blockIdx.z];
+    if ((int)(blockIdx.x * KBF_THREADS) >= pr.nq || pr.nt == 0) return;
+    const int per = (pr.nt + KBF_SPLITS - 1) / KBF_SPLITS;
+    const int t0 = blockIdx.y * per, t1 = min(pr.nt, t0 + per);
+    if (t0 >= t1) return;
+    const int q = blockIdx.x * KBF_THREADS + threadIdx.x;
+    const bool active = q < pr.nq;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    if (active) {
+        const uint4* qp = reinterpret_cast<const uint4*>(store + (size_t)(pr.q_start + q) * 32);
+        q0 = __ldg(qp); q1 = __ldg(qp + 1);
+    }
+    const uint4* tp = reinterpret_cast<const uint4*>(store + (size_t)pr.t_start * 32);
+    uint32_t key = 0xffffffffu;
+    for (int c0 = t0; c0 < t1; c0 += KBF_CHUNK) {
+        const int n = min(KBF_CHUNK, t1 - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n; i += KBF_THREADS) ts[i] = __ldg(tp + 2 * (size_t)c0 + i);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const int d = kf_ham256(q0, q1, ts[2 * j], ts[2 * j + 1]);
+            key = min(key, ((uint32_t)d << 16) | (uint32_t)(c0 + j));
+        }
+    }
+    if (active) atomicMin(&best[pr.out_start + q], key);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_frames, sfe_kfdb** out)
+{
+    if (!ctx || !bow || !out || capacity_frames < 1 || capacity_frames > (1 << 20)) return SFE_ERR_INVALID;
+    sfe_kfdb* d = new sfe_kfdb(); d->ctx = ctx; d->bow = bow;
+    d->cap_frames = capacity_frames; d->stride = ctx->pack.kp_cap; d->B = ctx->cfg.max_pairs;
+    d->nwords = bow->nwords; d->bm_words = (bow->nwords + 31) / 32;
+    const size_t F = capacity_frames, S = d->stride, B = d->B;
+    cudaError_t e = cudaSuccess;
+    auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    auto ah = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMallocHost(p, bytes); };
+    al((void**)&d->d_msub, F * S * 32); al((void**)&d->d_msub_n, F * 4);
+    al((void**)&d->d_dbw, F * S * 4); al((void**)&d->d_dbv, F * S * 8); al((void**)&d->d_dbn, F * 4);
+    al((void**)&d->d_word, B * S * 4); al((void**)&d->d_weight, B * S * 8);
+    al((void**)&d->d_bitmap, B * d->bm_words * 4); al((void**)&d->d_dense, B * (size_t)d->nwords * 8);
+    al((void**)&d->d_score, B * F * 8); al((void**)&d->d_common, B * F * 4);
+    al((void**)&d->d_qid, B * 4 * 4); al((void**)&d->d_qscore, B * 4 * 8); al((void**)&d->d_qn, B * 4);
+    al((void**)&d->d_pairs, B * KF_PAIRS * sizeof(BfPair)); al((void**)&d->d_pair_kf, B * KF_PAIRS * 4);
+    al((void**)&d->d_best, B * KF_PAIRS * S * 4);
+    ah((void**)&d->h_qid, B * 4 * 4); ah((void**)&d->h_qscore, B * 4 * 8); ah((void**)&d->h_qn, B * 4);
+    ah((void**)&d->h_pair_kf, B * KF_PAIRS * 4); ah((void**)&d->h_best, B * KF_PAIRS * S * 4); ah((void**)&d->h_msub_n, B * 4);
+    if (e == cudaSuccess) e = cudaMemset(d->d_bitmap, 0, B * d->bm_words * 4);
+    if (e == cudaSuccess) e = cudaMemset(d->d_dense, 0, B * (size_t)d->nwords * 8);
+    if (e == cudaSuccess) e = cudaMemset(d->d_msub_n, 0, F * 4);
+    if (e == cudaSuccess) e = cudaMemset(d->d_dbn, 0, F * 4);
+    if (e != cudaSuccess) { ctx->err = std::string("sfe_kfdb_create: ") + cudaGetErrorString(e); sfe_kfdb_destroy(d); return SFE_ERR_CUDA; }
+    cudaFuncSetAttribute(kf_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
+    cudaFuncSetAttribute(kf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KF_QT * d->bm_words * 4);
+    cudaGetLastError();
+    *out = d;
+    return SFE_OK;
+}
+
+extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
+{
+    if (!d) return;
+    cudaFree(d->d_msub); cudaFree(d->d_msub_n); cudaFree(d->d_dbw); cudaFree(d->d_dbv); cudaFree(d->d_dbn);
+    cudaFree(d->d_word); cudaFree(d->d_weight); cudaFree(d->d_bitmap); cudaFree(d->d_dense); cudaFree(d->d_score);
+    cudaFree(d->d_common); cudaFree(d->d_qid); cudaFree(d->d_qscore); cudaFree(d->d_qn); cudaFree(d->d_pairs);
+    cudaFree(d->d_pair_kf); cudaFree(d->d_best);
+    cudaFreeHost(d->h_qid); cudaFreeHost(d->h_qscore); cudaFreeHost(d->h_qn); cudaFreeHost(d->h_pair_kf); cudaFreeHost(d->h_best);
+    cudaFreeHost(d->h_msub_n);
+    delete d;
+}
+
+extern "C" int sfe_kfdb_size(const sfe_kfdb* d) { return d ? d->n_frames : 0; }
+extern "C" int sfe_kfdb_reset(sfe_kfdb* d) { if (!d) return SFE_ERR_INVALID; d->n_frames = 0; return SFE_OK; }
+
+extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
+{
+    if (!d || npairs < 1 || npairs > d->B) return SFE_ERR_INVALID;
+    sfe_context* c = d->ctx; sfe_bow* b = d->bow;
+    if (!c->have_results || c->last_npairs < npairs) { c->err = "sfe_kfdb_process_batch: process the stereo batch first"; return SFE_ERR_STATE; }
+    if (d->n_frames + npairs > d->cap_frames) { c->err = "keyframe store is full"; return SFE_ERR_CAPACITY; }
+    cudaStream_t s = c->stream;
+    const int cap = d->stride, base = d->n_frames, E = base + npairs;
+    // 1. matched-subset descriptors -> store
+    kf_gather_kernel<<<dim3((cap + 127) / 128, npairs), 256, 0, s>>>(c->d_desc, c->d_matches, c->d_match_count, cap, base, d->d_msub, d->d_msub_n);
+    // 2. words, 3. BoW vectors (into the database slots base .. base+npairs-1)
+    kf_transform_kernel<<<dim3((cap * 8 + 255) / 256, npairs), 256, 0, s>>>(b->d_first, b->d_nchild, b->d_desc, b->d_word, b->d_weight, b->depth,
+                                                                            c->d_desc, c->d_kp_count, cap, d->d_word, d->d_weight);
+    int np2 = 1; while (np2 < cap) np2 <<= 1;
+    if (np2 > 32768) { c->err = "keypoint capacity too large for the BoW vector kernel"; return SFE_ERR_INVALID; }
+    kf_vector_kernel<<<npairs, KV_THREADS, (size_t)np2 * 4, s>>>(d->d_word, d->d_weight, c->d_kp_count, cap, np2, base, d->d_dbw, d->d_dbv, d->d_dbn);
+    // 4-6. query: every frame against the entries older than itself
+    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, 0);
+    const int ne_vis = E - 1;                                   // entries any query of this batch can see
+    if (ne_vis > 0) {
+        kf_score_kernel<<<dim3((ne_vis + 7) / 8, (npairs + KF_QT - 1) / KF_QT), 256, (size_t)KF_QT * d->bm_words * 4, s>>>(
+            d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, d->cap_frames, d->d_score, d->d_common);
+    }
+    kf_topk_kernel<<<npairs, 256, 0, s>>>(d->d_score, d->d_common, base, d->cap_frames, 4, d->d_qid, d->d_qscore, d->d_qn);
+    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, 1);
+    // 7-8. data association: previous keyframe + BoW hits
+    kf_pairs_kernel<<<(npairs * KF_PAIRS + 127) / 128, 128, 0, s>>>(d->d_qid, d->d_qn, d->d_msub_n, base, npairs, cap, d->d_pairs, d->d_pair_kf);
+    KF_CUDA(d, cudaMemsetAsync(d->d_best, 0xff, (size_t)npairs * KF_PAIRS * cap * 4, s));
+    kf_bf_kernel<<<dim3((cap + KBF_THREADS - 1) / KBF_THREADS, KBF_SPLITS, npairs * KF_PAIRS), KBF_THREADS, 0, s>>>(d->d_msub, d->d_pairs, d->d_best);
+    c->launches += ne_vis > 0 ? 9 : 8;
+    KF_CUDA(d, cudaGetLastError());
+    d->last_base = base; d->last_n = npairs; d->n_frames = E;
+    return SFE_OK;
+}
+
+extern "C" int sfe_kfdb_results(sfe_kfdb* d, const int32_t** query_ids, const double** query_scores, const int32_t** query_n,
+                                const int32_t** pair_kf, const uint32_t** best, const int32_t** matched_n)
+{
+    if (!d) return SFE_ERR_INVALID;
+    cudaStream_t s = d->ctx->stream; const int n = d->last_n; const size_t cap = d->stride;
+    if (n == 0) { d->ctx->err = "no batch processed"; return SFE_ERR_STATE; }
+    KF_CUDA(d, cudaMemcpyAsync(d->h_qid, d->d_qid, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(d->h_qscore, d->d_qscore, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(d->h_qn, d->d_qn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(d->h_pair_kf, d->d_pair_kf, sizeof(int32_t) * KF_PAIRS * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(d->h_best, d->d_best, sizeof(uint32_t) * KF_PAIRS * n * cap, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(d->h_msub_n, d->d_msub_n + d->last_base, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaStreamSynchronize(s));
+    if (query_ids) *query_ids = d->h_qid; if (query_scores) *query_scores = d->h_qscore; if (query_n) *query_n = d->h_qn;
+    if (pair_kf) *pair_kf = d->h_pair_kf; if (best) *best = d->h_best; if (matched_n) *matched_n = d->h_msub_n;
+    return SFE_OK;
+}

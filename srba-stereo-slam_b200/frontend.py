@@ -91,6 +91,12 @@ def load_library():
     L.sfe_bow_db_query.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.sfe_bow_db_size.argtypes = [vp]
     L.sfe_bow_transform_device.argtypes = [vp, vp, i32, vp, vp]
+    L.sfe_kfdb_create.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    L.sfe_kfdb_destroy.argtypes = [vp]; L.sfe_kfdb_destroy.restype = None
+    L.sfe_kfdb_size.argtypes = [vp]
+    L.sfe_kfdb_reset.argtypes = [vp]
+    L.sfe_kfdb_process_batch.argtypes = [vp, i32]
+    L.sfe_kfdb_results.argtypes = [vp] + [C.POINTER(vp)] * 6
     _lib = L
     return L
 
@@ -299,3 +305,37 @@ class BowDatabase:
         return [(int(ids[i]), float(sc[i])) for i in range(n.value)]
 
     def size(self): return self.lib.sfe_bow_db_size(self.h)
+
+
+class KeyframeDatabase:
+    """Batched full front-end (sfe_kfdb_*): BoW query/add + keyframe store + data association for every pair of the
+    last processed stereo batch -- the per-keyframe sequence of EST.cpp:413-447 and :919, device-resident."""
+
+    def __init__(self, fe, bow, capacity_frames):
+        self.fe = fe; self.lib = fe.lib; self.bow = bow
+        h = C.c_void_p()
+        fe._chk(self.lib.sfe_kfdb_create(fe.h, bow.h, int(capacity_frames), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfe_kfdb_destroy(self.h); self.h = None
+
+    def size(self): return self.lib.sfe_kfdb_size(self.h)
+    def reset(self): self.fe._chk(self.lib.sfe_kfdb_reset(self.h))
+    def process_batch(self, npairs): self.fe._chk(self.lib.sfe_kfdb_process_batch(self.h, npairs))
+
+    def results(self, npairs):
+        """Returns dict of numpy arrays: query_ids [n,4], query_scores [n,4], query_n [n], pair_kf [n,5],
+        best [n,5,cap] (packed dist<<16 | train index, 0xFFFFFFFF = none), matched_n [n]."""
+        p = [C.c_void_p() for _ in range(6)]
+        self.fe._chk(self.lib.sfe_kfdb_results(self.h, *[C.byref(x) for x in p]))
+        n, cap = npairs, self.fe.kp_cap
+
+        def view(ptr, dtype, shape):
+            cnt = int(np.prod(shape))
+            buf = (C.c_uint8 * (cnt * np.dtype(dtype).itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dtype, cnt).reshape(shape).copy()
+        return {"query_ids": view(p[0], np.int32, (n, 4)), "query_scores": view(p[1], np.float64, (n, 4)),
+                "query_n": view(p[2], np.int32, (n,)), "pair_kf": view(p[3], np.int32, (n, 5)),
+                "best": view(p[4], np.uint32, (n, 5, cap)), "matched_n": view(p[5], np.int32, (n,))}
