@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the full front-end (BoW + KF match) measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -213,6 +214,58 @@ def main():
     cap = fe.kp_cap
     h2d = 2 * B * W * H
     d2h = 2 * B * cap * (28 + 32) + B * cap * 16 + 2 * B * 4 * 2 + B * 4
+
+    # ---- full front-end (BASELINE.json configs[2] shape): + BoW query/add + keyframe store + association -----
+    full = None
+    voc_path = os.path.join(ROOT, "tests", "golden", "voc_flat.npz")
+    if os.path.exists(voc_path) and not args.no_full:
+        vz = np.load(voc_path)
+        voc = {k: (vz[k] if vz[k].ndim else vz[k].item()) for k in vz.files}
+        bow = frontend.BowDatabase(fe, voc)
+        cap_frames = 4608                                       # >= KITTI-00's 4541 keyframes
+        kfdb = frontend.KeyframeDatabase(fe, bow, cap_frames)
+        steps_full = min(args.steps, (cap_frames // B) - 4)
+        prefill = (cap_frames // B) - steps_full - 1            # untimed batches so the timed ones see a large database
+        fe.upload(frames)
+        for _ in range(max(prefill, 3)):
+            fe.process_device(B); kfdb.process_batch(B)
+        fe.synchronize()
+        db0 = kfdb.size()
+        barrier()
+        fe.timer_start()
+        for _ in range(steps_full):
+            fe.process_device(B); kfdb.process_batch(B)
+        ms_full = fe.timer_stop()
+        barrier()
+        db1 = kfdb.size()
+        if dist is not None:
+            t = torch.tensor([ms_full], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_full = float(t.item())
+        # end to end: H2D + everything + D2H of stereo results and of query hits / association keys
+        kfdb.reset()
+        for f in fes:
+            f.submit_staged(B); kfdb.process_batch(B, src=f); f.wait_batch(); kfdb.results(B)
+        steps_e = min(steps_full, (cap_frames - kfdb.size()) // B)
+        barrier(); fe2.synchronize()
+        t0 = time.perf_counter()
+        fes[0].submit_staged(B); kfdb.process_batch(B, src=fes[0])
+        hits = 0
+        for s_ in range(steps_e):
+            if s_ + 1 < steps_e:
+                nx = fes[(s_ + 1) % 2]
+                nx.submit_staged(B); kfdb.process_batch(B, src=nx)
+            fes[s_ % 2].wait_batch()
+            if s_ + 1 == steps_e:
+                hits += int(kfdb.results(B)["query_n"].sum())      # results() syncs the database stream
+        fe2.synchronize(); barrier()
+        ms_full_e2e = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms_full_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_full_e2e = float(t.item())
+        full = {"metric": "stereo frames/sec, full front-end (extract + L/R match + BoW query/add + KF match vs previous + 4 hits)",
+                "value": world * B * steps_full / (ms_full * 1e-3), "ms_per_step": ms_full / steps_full,
+                "e2e": world * B * steps_e / (ms_full_e2e * 1e-3), "e2e_ms_per_step": ms_full_e2e / max(steps_e, 1),
+                "db_entries_during_timing": [db0, db1], "steps": steps_full, "e2e_steps": steps_e,
+                "note": "e2e downloads the association keys of the last batch only; stereo results every step"}
+        kfdb.close(); bow.close()
     fe2.close()
 
     # ---- per-kernel times, live (CUDA events around each stage, direct launches) --------------------------------
@@ -266,7 +319,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "stereo frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "matches_read_back": nmatch,
                         "timing": "host wall clock between full synchronisations; 2 contexts double-buffer PCIe against kernels"},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "full_frontend": full}
         print(json.dumps(line))
     fe.close()
     if dist is not None:

@@ -215,6 +215,9 @@ void sfe_kfdb_destroy(sfe_kfdb* db);
 int  sfe_kfdb_size(const sfe_kfdb* db);
 int  sfe_kfdb_reset(sfe_kfdb* db);
 int  sfe_kfdb_process_batch(sfe_kfdb* db, int npairs);     /* asynchronous on sfe_stream() */
+/* Same, taking the stereo batch of another context of the same GPU (double-buffered streaming): runs on that
+ * context's stream; successive batches are ordered on the database by an event. */
+int  sfe_kfdb_process_batch_on(sfe_kfdb* db, sfe_context* src, int npairs);
 int  sfe_kfdb_results(sfe_kfdb* db, const int32_t** query_ids /* [n][4] */, const double** query_scores /* [n][4] */,
                       const int32_t** query_n /* [n] */, const int32_t** pair_kf /* [n][5] */,
                       const uint32_t** best /* [n][5][capacity] */, const int32_t** matched_n /* [n] */);

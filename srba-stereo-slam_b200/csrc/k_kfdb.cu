@@ -17,7 +17,7 @@
 #include <algorithm>
 #include <cstring>
 
-#define KF_QT 16                 // queries per score CTA (bitmaps in shared memory)
+#define KF_QT 32                 // queries per score CTA (bitmaps in shared memory, one per lane)
 #define KF_PAIRS 5               // previous keyframe + 4 BoW hits (EST.cpp:426, :1758)
 
 struct BfPair { int q_start, nq, t_start, nt, out_start; };
@@ -35,6 +35,7 @@ struct sfe_kfdb {
     int32_t* h_qid = nullptr; double* h_qscore = nullptr; int32_t* h_qn = nullptr; int32_t* h_pair_kf = nullptr; uint32_t* h_best = nullptr;
     int32_t* h_msub_n = nullptr;
     int last_base = 0, last_n = 0;
+    cudaEvent_t ev_done = nullptr; bool ev_valid = false; cudaStream_t last_stream = nullptr;
 };
 
 #define KF_CUDA(d, call) SFE_CUDA((d)->ctx, call)
@@ -43,6 +44,25 @@ __device__ __forceinline__ int kf_ham256(const uint4& a0, const uint4& a1, const
 {
     return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// Same value with half the POPCs: the 8 xor words go through a carry-save adder tree (Harley-Seal), leaving
+// ones/twos/fours/eights planes -> 4 POPC + 14 LOP3 instead of 8 POPC.  The brute-force kernel is bound by the
+// POPC pipe (measured: 8 POPC per pair saturate it at ~44 % issue utilisation), LOP3 runs on the wider ALU pipe.
+#define KF_CSA(h, l, a, b, c) { const uint32_t u_ = (a) ^ (b); h = ((a) & (b)) | (u_ & (c)); l = u_ ^ (c); }
+__device__ __forceinline__ int kf_ham256_csa(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1)
+{
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    uint32_t t1, s1, t2, s2, t3, s3, f1, tw1, f2, tw2;
+    KF_CSA(t1, s1, x0, x1, x2);
+    KF_CSA(t2, s2, x3, x4, x5);
+    KF_CSA(t3, s3, s1, s2, x6);
+    const uint32_t ones = s3 ^ x7, t4 = s3 & x7;
+    KF_CSA(f1, tw1, t1, t2, t3);
+    const uint32_t twos = tw1 ^ t4; f2 = tw1 & t4; (void)tw2;
+    const uint32_t fours = f1 ^ f2, eights = f1 & f2;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
 }
 
 // ---- 1. gather the stereo-matched left descriptors of each pair into the keyframe store ----------------------
@@ -158,13 +178,37 @@ __global__ void kf_query_prep_kernel(const int32_t* __restrict__ dbw, const doub
     else { dense[(size_t)p * nwords + w] = dbv[(size_t)e * cap + i]; atomicOr(&bitmap[(size_t)p * bm_words + (w >> 5)], 1u << (w & 31)); }
 }
 
-// ---- 5. exact L1 scores: warp per database entry x 16 queries ---------------------------------------------------
-__global__ void __launch_bounds__(256)
+// ---- 5. exact L1 scores: lane = query (32 per CTA, bitmaps in shared memory), warp = database entry ------------
+// A warp stages the entry's sorted word list in shared memory with coalesced loads (all in flight at once), then
+// every lane walks it (broadcast LDS) testing its own query bitmap; on the ~2 % hits it gathers the query value
+// from the dense vector and accumulates in ascending word order = DBoW2's order (FP64, bit-identical).
+#define KS_WARPS 16
+#define KS_CHUNK 256
+#define KS_HQ 32                  // per-lane hit queue depth (a lane averages ~12 hits per entry)
+
+// Drains a lane's hit queue: the gathers of a group of 4 hits are issued together (memory-level parallelism),
+// the accumulation stays in queue (= ascending word) order.
+__device__ __forceinline__ double ks_flush(const uint32_t* hq, int cnt, const double* __restrict__ myq,
+                                           const double* __restrict__ ev, double s)
+{
+    for (int t = 0; t < cnt; t += 4) {
+        uint32_t h[4]; double qv[4], d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = t + k < cnt ? hq[(t + k) * 32] : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { qv[k] = t + k < cnt ? myq[h[k] >> 16] : 0.0; d[k] = t + k < cnt ? __ldg(ev + (h[k] & 0xffffu)) : 0.0; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (t + k < cnt) s += fabs(qv[k] - d[k]) - fabs(qv[k]) - fabs(d[k]);
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(KS_WARPS * 32)
 kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn, int cap,
                 int base, int nq, int nwords, int bm_words, const uint32_t* __restrict__ bitmap, const double* __restrict__ dense,
                 int score_stride, double* __restrict__ score, int32_t* __restrict__ common)
 {
-    extern __shared__ uint32_t bm[];                       // [KF_QT][bm_words]
+    extern __shared__ uint32_t bm[];            // [KF_QT][bm_words] | word staging [KS_WARPS][KS_CHUNK] | hit queues [KS_WARPS][KS_HQ][32]
     const int q0 = blockIdx.y * KF_QT;
     const int nqt = min(KF_QT, nq - q0);
     for (int i = threadIdx.x; i < KF_QT * bm_words; i += blockDim.x) {
@@ -172,40 +216,46 @@ kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv,
         bm[i] = q < nqt ? bitmap[(size_t)(q0 + q) * bm_words + (i - q * bm_words)] : 0u;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // queries of this tile see entries < base + q; the newest query of the tile bounds the useful entries
-    if (e >= base + q0 + nqt - 1) return;
-    const int n = dbn[e];
-    const int32_t* ew = dbw + (size_t)e * cap; const double* ev = dbv + (size_t)e * cap;
-    double s = 0.0; int any = 0;                            // lane q (< KF_QT) accumulates query q0+q
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        const int i = c0 + lane;
-        const int w = i < n ? __ldg(ew + i) : 0;
-        const double dv = i < n ? __ldg(ev + i) : 0.0;
-        uint32_t mine = 0;                                  // lane q keeps the hit mask of query q for this chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* wbuf = reinterpret_cast<int*>(bm + KF_QT * bm_words) + warp * KS_CHUNK;
+    uint32_t* hq = bm + KF_QT * bm_words + KS_WARPS * KS_CHUNK + warp * KS_HQ * 32 + lane;     // slot-major: conflict-free
+    const int q = q0 + lane;
+    const uint32_t* mybm = bm + lane * bm_words;           // bm_words is odd -> the 32 lanes hit 32 different banks
+    const double* myq = dense + (size_t)min(q, nq - 1) * nwords;
+    const int e_end = base + q0 + nqt - 1;                 // the newest query of the tile sees entries < e_end
+    for (int e = blockIdx.x * KS_WARPS + warp; e < e_end; e += gridDim.x * KS_WARPS) {
+        const int n = dbn[e];
+        const int32_t* ew = dbw + (size_t)e * cap;
+        const double* ev = dbv + (size_t)e * cap;
+        double s = 0.0; int any = 0, cnt = 0;
+        for (int c0 = 0; c0 < n; c0 += KS_CHUNK) {
+            const int m = min(KS_CHUNK, n - c0);
+            __syncwarp();
+#pragma unroll 4
+            for (int i = lane; i < m; i += 32) wbuf[i] = __ldg(ew + c0 + i);
+            __syncwarp();
+            // pad the staged chunk with a word no query contains is not possible (all words may occur), so the tail
+            // of the last group is masked by index instead
+            for (int i = 0; i < m; i += 4) {
+                const int4 w = *reinterpret_cast<const int4*>(wbuf + i);
+                const int ws[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
-        for (int q = 0; q < KF_QT; ++q) {
-            const bool hit = i < n && ((bm[q * bm_words + (w >> 5)] >> (w & 31)) & 1u);
-            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-            if (lane == q) mine = bal;
-        }
-        while (__any_sync(0xffffffffu, mine != 0u)) {       // replay hits in ascending word order
-            const int src = mine ? __ffs(mine) - 1 : 0;
-            const int ws = __shfl_sync(0xffffffffu, w, src);
-            const double ds = __shfl_sync(0xffffffffu, dv, src);
-            if (mine) {
-                const double qv = dense[(size_t)(q0 + lane) * nwords + ws];
-                s += fabs(qv - ds) - fabs(qv) - fabs(ds);
-                any = 1; mine &= mine - 1;
+                for (int k = 0; k < 4; ++k) {
+                    // branch-free push: always store to the current slot, advance only on a hit
+                    const uint32_t hit = (i + k < m) ? ((mybm[ws[k] >> 5] >> (ws[k] & 31)) & 1u) : 0u;
+                    hq[cnt * 32] = ((uint32_t)ws[k] << 16) | (uint32_t)(c0 + i + k);
+                    cnt += (int)hit;
+                }
+                if (__any_sync(0xffffffffu, cnt > KS_HQ - 5)) {      // warp-uniform drain: every lane flushes what it has
+                    if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; cnt = 0; }
+                }
             }
         }
-    }
-    if (lane < nqt) {
-        const int q = q0 + lane;
-        const bool visible = e < base + q;                 // a frame only sees older entries
-        score[(size_t)q * score_stride + e] = s;
-        common[(size_t)q * score_stride + e] = (any && visible) ? 1 : 0;
+        if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; }
+        if (lane < nqt) {
+            score[(size_t)q * score_stride + e] = s;
+            common[(size_t)q * score_stride + e] = (any && e < base + q) ? 1 : 0;     // a frame only sees older entries
+        }
     }
 }
 
@@ -288,7 +338,7 @@ kf_bf_kernel(const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < n; ++j) {
-            const int d = kf_ham256(q0, q1, ts[2 * j], ts[2 * j + 1]);
+            const int d = kf_ham256_csa(q0, q1, ts[2 * j], ts[2 * j + 1]);
             key = min(key, ((uint32_t)d << 16) | (uint32_t)(c0 + j));
         }
     }
@@ -316,13 +366,14 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     al((void**)&d->d_best, B * KF_PAIRS * S * 4);
     ah((void**)&d->h_qid, B * 4 * 4); ah((void**)&d->h_qscore, B * 4 * 8); ah((void**)&d->h_qn, B * 4);
     ah((void**)&d->h_pair_kf, B * KF_PAIRS * 4); ah((void**)&d->h_best, B * KF_PAIRS * S * 4); ah((void**)&d->h_msub_n, B * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemset(d->d_bitmap, 0, B * d->bm_words * 4);
     if (e == cudaSuccess) e = cudaMemset(d->d_dense, 0, B * (size_t)d->nwords * 8);
     if (e == cudaSuccess) e = cudaMemset(d->d_msub_n, 0, F * 4);
     if (e == cudaSuccess) e = cudaMemset(d->d_dbn, 0, F * 4);
     if (e != cudaSuccess) { ctx->err = std::string("sfe_kfdb_create: ") + cudaGetErrorString(e); sfe_kfdb_destroy(d); return SFE_ERR_CUDA; }
     cudaFuncSetAttribute(kf_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
-    cudaFuncSetAttribute(kf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KF_QT * d->bm_words * 4);
+    cudaFuncSetAttribute(kf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KF_QT * d->bm_words * 4 + KS_WARPS * (KS_CHUNK + KS_HQ * 32) * 4);
     cudaGetLastError();
     *out = d;
     return SFE_OK;
@@ -337,19 +388,31 @@ extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
     cudaFree(d->d_pair_kf); cudaFree(d->d_best);
     cudaFreeHost(d->h_qid); cudaFreeHost(d->h_qscore); cudaFreeHost(d->h_qn); cudaFreeHost(d->h_pair_kf); cudaFreeHost(d->h_best);
     cudaFreeHost(d->h_msub_n);
+    if (d->ev_done) cudaEventDestroy(d->ev_done);
     delete d;
 }
 
 extern "C" int sfe_kfdb_size(const sfe_kfdb* d) { return d ? d->n_frames : 0; }
 extern "C" int sfe_kfdb_reset(sfe_kfdb* d) { if (!d) return SFE_ERR_INVALID; d->n_frames = 0; return SFE_OK; }
 
+extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* src, int npairs);
+
 extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
 {
-    if (!d || npairs < 1 || npairs > d->B) return SFE_ERR_INVALID;
-    sfe_context* c = d->ctx; sfe_bow* b = d->bow;
+    return d ? sfe_kfdb_process_batch_on(d, d->ctx, npairs) : SFE_ERR_INVALID;
+}
+
+// Runs on the SOURCE context's stream (so that context's next batch cannot overwrite the descriptors being read);
+// batches from different contexts are serialised on the database through an event.
+extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs)
+{
+    if (!d || !c || npairs < 1 || npairs > d->B) return SFE_ERR_INVALID;
+    if (c->pack.kp_cap != d->stride || c->cfg.device != d->ctx->cfg.device) { c->err = "source context does not match the keyframe database"; return SFE_ERR_INVALID; }
+    sfe_bow* b = d->bow;
     if (!c->have_results || c->last_npairs < npairs) { c->err = "sfe_kfdb_process_batch: process the stereo batch first"; return SFE_ERR_STATE; }
     if (d->n_frames + npairs > d->cap_frames) { c->err = "keyframe store is full"; return SFE_ERR_CAPACITY; }
     cudaStream_t s = c->stream;
+    if (d->ev_valid && d->last_stream != s) KF_CUDA(d, cudaStreamWaitEvent(s, d->ev_done, 0));
     const int cap = d->stride, base = d->n_frames, E = base + npairs;
     // 1. matched-subset descriptors -> store
     kf_gather_kernel<<<dim3((cap + 127) / 128, npairs), 256, 0, s>>>(c->d_desc, c->d_matches, c->d_match_count, cap, base, d->d_msub, d->d_msub_n);
@@ -363,7 +426,9 @@ extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
     kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, 0);
     const int ne_vis = E - 1;                                   // entries any query of this batch can see
     if (ne_vis > 0) {
-        kf_score_kernel<<<dim3((ne_vis + 7) / 8, (npairs + KF_QT - 1) / KF_QT), 256, (size_t)KF_QT * d->bm_words * 4, s>>>(
+        const int tiles = (npairs + KF_QT - 1) / KF_QT;
+        const int gx = std::max(1, std::min((ne_vis + KS_WARPS - 1) / KS_WARPS, (148 + tiles - 1) / tiles));   // one CTA per SM (129 KB of bitmaps each)
+        kf_score_kernel<<<dim3(gx, tiles), KS_WARPS * 32, (size_t)KF_QT * d->bm_words * 4 + (size_t)KS_WARPS * (KS_CHUNK + KS_HQ * 32) * 4, s>>>(
             d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, d->cap_frames, d->d_score, d->d_common);
     }
     kf_topk_kernel<<<npairs, 256, 0, s>>>(d->d_score, d->d_common, base, d->cap_frames, 4, d->d_qid, d->d_qscore, d->d_qn);
@@ -374,6 +439,8 @@ extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
     kf_bf_kernel<<<dim3((cap + KBF_THREADS - 1) / KBF_THREADS, KBF_SPLITS, npairs * KF_PAIRS), KBF_THREADS, 0, s>>>(d->d_msub, d->d_pairs, d->d_best);
     c->launches += ne_vis > 0 ? 9 : 8;
     KF_CUDA(d, cudaGetLastError());
+    KF_CUDA(d, cudaEventRecord(d->ev_done, s));
+    d->ev_valid = true; d->last_stream = s;
     d->last_base = base; d->last_n = npairs; d->n_frames = E;
     return SFE_OK;
 }
@@ -382,7 +449,7 @@ extern "C" int sfe_kfdb_results(sfe_kfdb* d, const int32_t** query_ids, const do
                                 const int32_t** pair_kf, const uint32_t** best, const int32_t** matched_n)
 {
     if (!d) return SFE_ERR_INVALID;
-    cudaStream_t s = d->ctx->stream; const int n = d->last_n; const size_t cap = d->stride;
+    cudaStream_t s = d->last_stream ? d->last_stream : d->ctx->stream; const int n = d->last_n; const size_t cap = d->stride;
     if (n == 0) { d->ctx->err = "no batch processed"; return SFE_ERR_STATE; }
     KF_CUDA(d, cudaMemcpyAsync(d->h_qid, d->d_qid, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, s));
     KF_CUDA(d, cudaMemcpyAsync(d->h_qscore, d->d_qscore, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, s));

@@ -96,6 +96,7 @@ def load_library():
     L.sfe_kfdb_size.argtypes = [vp]
     L.sfe_kfdb_reset.argtypes = [vp]
     L.sfe_kfdb_process_batch.argtypes = [vp, i32]
+    L.sfe_kfdb_process_batch_on.argtypes = [vp, vp, i32]
     L.sfe_kfdb_results.argtypes = [vp] + [C.POINTER(vp)] * 6
     _lib = L
     return L
@@ -323,7 +324,12 @@ class KeyframeDatabase:
 
     def size(self): return self.lib.sfe_kfdb_size(self.h)
     def reset(self): self.fe._chk(self.lib.sfe_kfdb_reset(self.h))
-    def process_batch(self, npairs): self.fe._chk(self.lib.sfe_kfdb_process_batch(self.h, npairs))
+    def process_batch(self, npairs, src=None):
+        """src: the StereoFrontEnd whose last batch is consumed (default: the one the database was created on)."""
+        if src is None:
+            self.fe._chk(self.lib.sfe_kfdb_process_batch(self.h, npairs))
+        else:
+            src._chk(self.lib.sfe_kfdb_process_batch_on(self.h, src.h, npairs))
 
     def results(self, npairs):
         """Returns dict of numpy arrays: query_ids [n,4], query_scores [n,4], query_n [n], pair_kf [n,5],

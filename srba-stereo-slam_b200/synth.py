@@ -143,10 +143,27 @@ class CorridorScene:
         return out
 
 
-def stereo_batch(npairs, width=1241, height=376, seed=0, unique=None):
-    """[npairs, 2, H, W] uint8: `unique` rendered frames (default min(npairs, 8)) tiled to npairs."""
+def stereo_batch(npairs, width=1241, height=376, seed=0, unique=None, augment=True):
+    """[npairs, 2, H, W] uint8.  `unique` frames (default min(npairs, 8)) are rendered; with `augment` each is also
+    mirrored horizontally (left/right swapped so disparities stay positive), flipped vertically and intensity-inverted,
+    giving 8 distinct valid rectified stereo pairs per rendered frame (different descriptors and BoW words) before the
+    set is tiled to npairs.  Rendering 1241x376 costs ~1.6 s per image, hence the reuse."""
     unique = min(npairs, 8) if unique is None else min(unique, npairs)
     sc = CorridorScene(seed=seed, width=width, height=height)
     base = sc.sequence(unique)
-    reps = (npairs + unique - 1) // unique
+    if augment:
+        var = []
+        for inv in (False, True):
+            for vf in (False, True):
+                for hf in (False, True):
+                    v = base
+                    if hf:
+                        v = v[:, ::-1, :, ::-1]            # mirror columns and swap the two views
+                    if vf:
+                        v = v[:, :, ::-1, :]
+                    if inv:
+                        v = 255 - v
+                    var.append(v)
+        base = np.stack(var, 1).reshape(-1, 2, height, width)   # frame-major: consecutive pairs are different scenes
+    reps = (npairs + len(base) - 1) // len(base)
     return np.ascontiguousarray(np.tile(base, (reps, 1, 1, 1))[:npairs])
