@@ -20,7 +20,7 @@ __constant__ int c_umax[16] = { 15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 
 
 #define DESC_WARPS 8
 #define PATCH_R 18
-#define PATCH_PITCH 40
+#define PATCH_PITCH 44      // 11 words: the 37-byte row plus up to 3 bytes of alignment slack on the left
 
 __device__ __forceinline__ float cv_fast_atan2(float y, float x)
 {
@@ -52,7 +52,7 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
                 sfe_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ kp_count)
 {
     __shared__ uint32_t pat_s[256];                                   // [test-in-byte j][lane] -> char4
-    __shared__ uint8_t patch_s[DESC_WARPS][(2 * PATCH_R + 1) * PATCH_PITCH];
+    __shared__ alignas(16) uint8_t patch_s[DESC_WARPS][(2 * PATCH_R + 1) * PATCH_PITCH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
     {   // pattern entry t = 8*L + j  ->  pat_s[j*32 + L]
@@ -82,20 +82,19 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
     const int pitch = g.pitch;
 
     // ---- orientation: m10 = sum u*I, m01 = sum v*I over the radius-15 disc ------------------
+    // lane = column u; the disc is symmetric (umax[umax[v]] >= v), so column u spans rows |v| <= umax[|u|]
     int m10 = 0, m01 = 0;
     {
         const int u = lane - 15;
-        if (lane < 31) {
-            const uint8_t* c = im + (size_t)y * pitch + x + u;
-            const int au = abs(u);
-#pragma unroll 4
-            for (int v = -15; v <= 15; ++v) {
-                if (au <= c_umax[abs(v)]) {
-                    const int I = __ldg(c + v * pitch);
-                    m10 += u * I; m01 += v * I;
-                }
-            }
+        const int vm = lane < 31 ? c_umax[abs(u)] : -1;
+        const uint8_t* p = im + (size_t)(y - 15) * pitch + x + u;
+        int sum = 0;
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) {
+            if (abs(v) <= vm) { const int I = __ldg(p); sum += I; m01 += v * I; }
+            p += pitch;
         }
+        m10 = u * sum;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -104,19 +103,27 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
     }
     const float angle = cv_fast_atan2((float)m01, (float)m10);
 
-    // ---- stage the blurred 37x37 patch -----------------------------------------------------
+    // ---- stage the blurred 37x37 patch with aligned 32-bit loads: 37 rows x 11 words ----------------
     uint8_t* ps = patch_s[warp];
-    for (int r = 0; r < 2 * PATCH_R + 1; ++r) {
-        const uint8_t* row = bl + (size_t)(y - PATCH_R + r) * pitch + (x - PATCH_R);
-        ps[r * PATCH_PITCH + lane] = __ldg(row + lane);
-        if (lane < 2 * PATCH_R + 1 - 32) ps[r * PATCH_PITCH + 32 + lane] = __ldg(row + 32 + lane);
+    const int xa = (x - PATCH_R) & ~3, xsh = (x - PATCH_R) - xa;
+    {
+        const uint8_t* b0 = bl + (size_t)(y - PATCH_R) * pitch + xa;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < (2 * PATCH_R + 1) * 11) {
+                const int row = idx / 11, col = idx - row * 11;
+                reinterpret_cast<uint32_t*>(ps)[row * (PATCH_PITCH / 4) + col] =
+                    __ldg(reinterpret_cast<const uint32_t*>(b0 + (size_t)row * pitch) + col);
+            }
+        }
     }
     __syncwarp();
 
     // ---- 256 tests, 8 per lane -------------------------------------------------------------
     const float arad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     const float ca = (float)cos((double)arad), sa = (float)sin((double)arad);
-    const uint8_t* ctr = ps + PATCH_R * PATCH_PITCH + PATCH_R;
+    const uint8_t* ctr = ps + PATCH_R * PATCH_PITCH + PATCH_R + xsh;
     uint32_t byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

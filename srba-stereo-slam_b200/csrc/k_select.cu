@@ -9,9 +9,12 @@
 // radix select.  Survivors are written in canonical order (y, then x) -- the reference's own order
 // is an std::nth_element artefact, so parity is defined on this order.
 //
-// One CTA per (image, level).  Warp-shuffle reductions for the 7x7 Harris sums (integer, exact);
+// One CTA per (image, level).  Harris: one thread per candidate, 9x9 window via aligned word loads and a
+// 3-row sliding register window (integer sums, exact); survivors bitonic-sorted in shared memory;
 // the float expression is evaluated unfused (__fmul_rn/__fsub_rn) to match the CPU bit for bit.
 #include "sfe_internal.cuh"
+
+#define SEL_SORT_CAP 1024
 
 __device__ __forceinline__ uint32_t float_order_key(float f)   // monotone map float -> uint32
 {
@@ -72,37 +75,44 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     int nc = s_n;
     if (nc > cand_cap) { nc = cand_cap; if (tid == 0) atomicOr(&status[img], SFE_ERR_CAPACITY); }
 
-    // ---- Harris response, one warp per candidate ------------------------------------------
+    // ---- Harris response, one thread per candidate: 9x9 window through a 3-row sliding register window ----
     const uint8_t* im = pyr + g.lvl_ofs + (size_t)img * g.img_bytes;
     const int pitch = g.pitch;
-    for (int c = warp; c < nc; c += SEL_THREADS / 32) {
+    for (int c = tid; c < nc; c += SEL_THREADS) {
         const int x = cand_xy[c] & 0xffff, y = cand_xy[c] >> 16;
+        const uint8_t* rowp = im + (size_t)(y - 4) * pitch + (x - 4);
+        const int sh = (int)((size_t)rowp & 3) * 8;                      // pitch % 4 == 0: same alignment on every row
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp - (sh >> 3));
+        int r0[9], r1[9], r2[9];
+        auto load_row = [&](int* r, int i) {
+            const uint32_t* w = wp + (size_t)i * (pitch >> 2);
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+            const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh);
+            r[0] = a & 0xff; r[1] = (a >> 8) & 0xff; r[2] = (a >> 16) & 0xff; r[3] = a >> 24;
+            r[4] = b & 0xff; r[5] = (b >> 8) & 0xff; r[6] = (b >> 16) & 0xff; r[7] = b >> 24;
+            r[8] = (w2 >> sh) & 0xff;                                    // ninth byte: bits [sh, sh+8) of the third word
+        };
+        load_row(r0, 0); load_row(r1, 1);
         int a = 0, b = 0, cc = 0;
-        for (int k = lane; k < 49; k += 32) {
-            const int i = k / 7, j = k - i * 7;
-            const uint8_t* p = im + (size_t)(y - 3 + i) * pitch + (x - 3 + j);
-            const int p00 = __ldg(p - pitch - 1), p01 = __ldg(p - pitch), p02 = __ldg(p - pitch + 1);
-            const int p10 = __ldg(p - 1), p12 = __ldg(p + 1);
-            const int p20 = __ldg(p + pitch - 1), p21 = __ldg(p + pitch), p22 = __ldg(p + pitch + 1);
-            const int Ix = (p12 - p10) * 2 + (p02 - p00) + (p22 - p20);
-            const int Iy = (p21 - p01) * 2 + (p20 - p00) + (p22 - p02);
-            a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-            cc += __shfl_xor_sync(0xffffffffu, cc, o);
+        for (int i = 0; i < 7; ++i) {
+            load_row(r2, i + 2);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int Ix = (r1[j + 2] - r1[j]) * 2 + (r0[j + 2] - r0[j]) + (r2[j + 2] - r2[j]);
+                const int Iy = (r2[j + 1] - r0[j + 1]) * 2 + (r2[j] - r0[j]) + (r2[j + 2] - r0[j + 2]);
+                a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+            }
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
         }
-        if (lane == 0) {
-            float scale = __fdiv_rn(1.0f, 4.0f * 7.0f * 255.0f);
-            const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
-            const float fa = (float)a, fb = (float)b, fc = (float)cc;
-            const float t3 = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
-            const float s = __fadd_rn(fa, fb);
-            const float t5 = __fmul_rn(__fmul_rn(0.04f, s), s);
-            cand_resp[c] = __fmul_rn(__fsub_rn(t3, t5), s4);
-        }
+        const float scale = __fdiv_rn(1.0f, 4.0f * 7.0f * 255.0f);
+        const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+        const float fa = (float)a, fb = (float)b, fc = (float)cc;
+        const float t3 = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
+        const float sm = __fadd_rn(fa, fb);
+        const float t5 = __fmul_rn(__fmul_rn(0.04f, sm), sm);
+        cand_resp[c] = __fmul_rn(__fsub_rn(t3, t5), s4);
     }
     __syncthreads();
 
@@ -134,22 +144,51 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
         nc = 0;
     }
 
-    // ---- canonical order: rank kept points by (y, x) --------------------------------------
+    // ---- canonical order (y, then x): compact the kept points, bitonic sort on the packed key -----------
     uint32_t* out_xy = sel_xy + (size_t)img * P.sel_img_stride + g.sel_ofs;
     float* out_r = sel_resp + (size_t)img * P.sel_img_stride + g.sel_ofs;
+    __shared__ uint32_t skey[SEL_SORT_CAP];
+    __shared__ float sval[SEL_SORT_CAP];
     if (tid == 0) s_n = 0;
     __syncthreads();
+    int nkept_local = 0;
     for (int i = tid; i < nc; i += SEL_THREADS) {
         if (!(cand_resp[i] >= boundary)) continue;
-        const uint32_t key = cand_xy[i];
-        int rank = 0;
-        for (int j = 0; j < nc; ++j) rank += (cand_resp[j] >= boundary) && (cand_xy[j] < key);
-        atomicAdd(&s_n, 1);
-        if (rank < g.sel_cap) { out_xy[rank] = key; out_r[rank] = cand_resp[i]; }
+        const int slot = atomicAdd(&s_n, 1);
+        if (slot < SEL_SORT_CAP) { skey[slot] = cand_xy[i]; sval[slot] = cand_resp[i]; }
+        ++nkept_local;
     }
     __syncthreads();
+    const int nk_all = s_n;
+    if (nk_all <= SEL_SORT_CAP) {
+        int np2 = 1; while (np2 < nk_all) np2 <<= 1;
+        for (int i = nk_all + tid; i < np2; i += SEL_THREADS) { skey[i] = 0xffffffffu; sval[i] = 0.f; }
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += SEL_THREADS) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t ka = skey[i], kb = skey[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((ka > kb) == up) { skey[i] = kb; skey[ixj] = ka; const float t = sval[i]; sval[i] = sval[ixj]; sval[ixj] = t; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = tid; i < min(nk_all, g.sel_cap); i += SEL_THREADS) { out_xy[i] = skey[i]; out_r[i] = sval[i]; }
+    } else {
+        // very large quotas: rank by counting (O(n^2), exact)
+        for (int i = tid; i < nc; i += SEL_THREADS) {
+            if (!(cand_resp[i] >= boundary)) continue;
+            const uint32_t key = cand_xy[i];
+            int rank = 0;
+            for (int j = 0; j < nc; ++j) rank += (cand_resp[j] >= boundary) && (cand_xy[j] < key);
+            if (rank < g.sel_cap) { out_xy[rank] = key; out_r[rank] = cand_resp[i]; }
+        }
+    }
     if (tid == 0) {
-        int nk = s_n;
+        int nk = nk_all;
         if (nk > g.sel_cap) { nk = g.sel_cap; atomicOr(&status[img], SFE_ERR_CAPACITY); }
         sel_count[(size_t)img * P.nlevels + level] = nk;
     }
