@@ -188,25 +188,40 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H every step) -------------------------
-    # Two contexts used alternately (the documented streaming usage of sfe_submit_batch_host / sfe_wait_batch):
+    # Three contexts used round-robin (the documented streaming usage of sfe_submit_batch_host / sfe_wait_batch):
     # one batch's PCIe traffic overlaps the other's kernels.  Inputs live in pinned host memory; every step copies
     # its 2*B images to the device and its keypoints/descriptors/matches/counts back.
-    fe2 = frontend.StereoFrontEnd(width=W, height=H, nlevels=NLEVELS, nfeatures=NFEAT, max_pairs=B, device=local)
-    fe2.host_staging()[:2 * B] = frames.reshape(-1, H, W)
-    fes = (fe, fe2)
+    NCTX = 3
+    extra = [frontend.StereoFrontEnd(width=W, height=H, nlevels=NLEVELS, nfeatures=NFEAT, max_pairs=B, device=local) for _ in range(NCTX - 1)]
+    fe2 = extra[0]
+    for f in extra:
+        f.host_staging()[:2 * B] = frames.reshape(-1, H, W)
+    fes = (fe,) + tuple(extra)
+
+    def sync_all():
+        for f in fes:
+            f.synchronize()
+        barrier()
     for f in fes:
         f.submit_staged(B); f.wait_batch()
-    barrier(); fe2.synchronize()
+    sync_all()
+    # link speed for context: one pinned->device copy of a step's images, timed alone
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fe.upload(stage[:2 * B].reshape(B, 2, H, W))
+    h2d_gbs = 5 * 2 * B * W * H / (time.perf_counter() - t0) / 1e9
+    sync_all()
     nmatch = 0
     t0 = time.perf_counter()
-    fes[0].submit_staged(B)
+    for k_ in range(min(NCTX - 1, args.steps)):
+        fes[k_].submit_staged(B)
     for s_ in range(args.steps):
-        if s_ + 1 < args.steps:
-            fes[(s_ + 1) % 2].submit_staged(B)
-        ptrs = fes[s_ % 2].wait_batch()
+        if s_ + NCTX - 1 < args.steps:
+            fes[(s_ + NCTX - 1) % NCTX].submit_staged(B)
+        ptrs = fes[s_ % NCTX].wait_batch()
         cnt = np.frombuffer((4 * 4 * B * __import__("ctypes").c_uint8).from_address(ptrs[3].value), np.int32).reshape(B, 4)
         nmatch += int(cnt[:, 2].sum())                      # the host reads the step's result
-    fe2.synchronize(); barrier()
+    sync_all()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     if dist is not None:
         t = torch.tensor([ms_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.item())
@@ -242,6 +257,7 @@ def main():
             t = torch.tensor([ms_full], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_full = float(t.item())
         # end to end: H2D + everything + D2H of stereo results and of query hits / association keys
         kfdb.reset()
+        fes = fes[:2]
         for f in fes:
             f.submit_staged(B); kfdb.process_batch(B, src=f); f.wait_batch(); kfdb.results(B)
         steps_e = min(steps_full, (cap_frames - kfdb.size()) // B)
@@ -266,7 +282,8 @@ def main():
                 "db_entries_during_timing": [db0, db1], "steps": steps_full, "e2e_steps": steps_e,
                 "note": "e2e downloads the association keys of the last batch only; stereo results every step"}
         kfdb.close(); bow.close()
-    fe2.close()
+    for f in extra:
+        f.close()
 
     # ---- per-kernel times, live (CUDA events around each stage, direct launches) --------------------------------
     fe.set_profiling(True)
@@ -318,7 +335,8 @@ def main():
                            "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world},
                 "e2e": {"value": e2e, "unit": "stereo frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "matches_read_back": nmatch,
-                        "timing": "host wall clock between full synchronisations; 2 contexts double-buffer PCIe against kernels"},
+                        "h2d_link_GBps_measured": h2d_gbs,
+                        "timing": "host wall clock between full synchronisations; 3 contexts pipeline PCIe against kernels"},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "full_frontend": full}
         print(json.dumps(line))
     fe.close()

@@ -104,32 +104,24 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
                 }
             }
         }
-        // one warp-level compaction for the (up to 12) flagged bytes of each lane
-        const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            int wbase = 0;
-            if (lane == 31) wbase = atomicAdd(&n1, total);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            int o = wbase + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int idx4 = (tid + 256 * k) * 4;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (m[k] & (0x80u << (8 * b))) list1[o++] = (uint16_t)(idx4 + b);
-            }
+        // compaction: the 12 byte flags of this thread fold into a 12-bit mask; one shared atomic per thread
+        // that has survivors (ptxas aggregates same-address atomics across the warp), then a short bit loop
+        uint32_t cm = nibble_of_flags(m[0]) | (nibble_of_flags(m[1]) << 4) | (nibble_of_flags(m[2]) << 8);
+        if (cm) {
+            int o = atomicAdd(&n1, __popc(cm));
+            do {
+                const int b = __ffs(cm) - 1;
+                cm &= cm - 1;
+                list1[o++] = (uint16_t)((tid + 256 * (b >> 2)) * 4 + (b & 3));
+            } while (cm);
         }
     }
     __syncthreads();
 
     // ---- B1: exact FAST-9 test on the survivors; the 16 ring bytes are packed 4 per word and compared SWAR ----
     const int nc1 = n1;
-    for (int base = 0; base < nc1; base += 256) {
-        const int i = base + tid;
+    for (int base = (tid >> 5) * 32; base < nc1; base += 256) {        // warp-strided: idle warps skip the loop
+        const int i = base + lane;
         bool corner = false; uint32_t entry = 0;
         if (i < nc1) {
             const int pos = list1[i];
@@ -194,8 +186,8 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     uint32_t* out = raw + (size_t)img * P.raw_img_stride + g.raw_ofs;
     const int SPB = FAST_WJ * 4;
     const int y_end = min(ty0 + FAST_TH, g.ry1);
-    for (int base = 0; base < nc2; base += 256) {
-        const int i = base + tid;
+    for (int base = (tid >> 5) * 32; base < nc2; base += 256) {        // warp-strided: idle warps skip the loop
+        const int i = base + lane;
         bool keep = false; int px = 0, py = 0, sc = 0;
         if (i < nc2) {
             const int pos = list2[i] & 0x7fff;
