@@ -8,7 +8,7 @@
 //   SFE_BLUR_FLOAT       float taps, float row pass accumulated left to right, symmetric float column
 //                        pass, round-half-even -- cv::sepFilter2D since OpenCV 3.4 (what cv2 4.13's ORB
 //                        runs; pinned bit-exactly by tests/golden).
-// One launch covers all levels and images.  A CTA stages a 134x22 footprint with one 3-D TMA load;
+// One launch covers all levels and images.  A CTA stages a 134x38 footprint with one 3-D TMA load;
 // border tiles patch the reflect-101 halo inside shared memory (TMA zero-fills outside the image), so the
 // passes are branch-free: the fixed-point row pass is two DP4A per output on byte-permuted words, the
 // column pass works on 4x4 register blocks and stores packed 32-bit words.
@@ -28,12 +28,12 @@ __device__ __forceinline__ int row7_dp4a(uint32_t lo4, uint32_t hi4)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint8_t* __restrict__ blur)
 {
     __shared__ alignas(128) uint8_t tile[BLUR_BOX_H * BLUR_BOX_W];
     __shared__ alignas(8) uint64_t bar;
-    __shared__ alignas(16) int rowbuf[22 * BLUR_TW];
+    __shared__ alignas(16) int rowbuf[BLUR_ROWS * BLUR_TW];
 
     const int tid = threadIdx.x;
     const int4 ti = __ldg(tile_tab + blockIdx.x);
@@ -52,10 +52,10 @@ blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     mbar_wait(&bar, 0);
 
     // ---- reflect-101 fix-up, border tiles only (TMA zero-filled what lies outside the image) ----------
-    // tile row r <-> image row y0-3+r (r < 22 used); tile byte c <-> image column bx0+c
+    // tile row r <-> image row y0-3+r (r < BLUR_ROWS used); tile byte c <-> image column bx0+c
     const bool bl = x0 == 0, br = x0 + BLUR_TW + 3 > w, bt = y0 == 0, bb = y0 + BLUR_TH + 3 > h;
     if (bl || br) {                                // columns first (rows still raw)
-        for (int i = tid; i < 22 * 8; i += 256) {
+        for (int i = tid; i < BLUR_ROWS * 8; i += 256) {
             const int r = i >> 3, k = i & 7;
             uint8_t* row = tile + r * BLUR_BOX_W;
             if (bl && k < 3) row[16 - 1 - k] = row[16 + 1 + k];                       // x = -1-k  <- x = 1+k
@@ -71,7 +71,7 @@ blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
             if (bt && k < 3) tw[(3 - 1 - k) * (BLUR_BOX_W / 4) + cw] = tw[(3 + 1 + k) * (BLUR_BOX_W / 4) + cw];   // y = -1-k <- 1+k
             if (bb && k >= 3) {
                 const int y = h + (k - 3), r = y - (y0 - 3), rs = 2 * h - 2 - y - (y0 - 3);
-                if (r >= 0 && r < 22 && rs >= 0) tw[r * (BLUR_BOX_W / 4) + cw] = tw[rs * (BLUR_BOX_W / 4) + cw];
+                if (r >= 0 && r < BLUR_ROWS && rs >= 0) tw[r * (BLUR_BOX_W / 4) + cw] = tw[rs * (BLUR_BOX_W / 4) + cw];
             }
         }
         __syncthreads();
@@ -80,7 +80,7 @@ blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     // ---- row pass: 4 adjacent outputs per thread from 3 aligned words ------------------------------------
     {
         const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile) + 3;      // word 3 = pixels x0-4 .. x0-1
-        for (int i = tid; i < 22 * (BLUR_TW / 4); i += 256) {
+        for (int i = tid; i < BLUR_ROWS * (BLUR_TW / 4); i += 256) {
             const int r = i >> 5, q = i & 31;
             const uint32_t* c = tw + r * (BLUR_BOX_W / 4) + q;
             const uint32_t A = c[0], B = c[1], C = c[2];                       // pixels x-4..x-1 | x..x+3 | x+4..x+7

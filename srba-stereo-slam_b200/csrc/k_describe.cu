@@ -45,7 +45,7 @@ __device__ __forceinline__ float cv_fast_atan2(float y, float x)
     return a;
 }
 
-__global__ void __launch_bounds__(DESC_WARPS * 32)
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6)
 describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                 const uint32_t* __restrict__ sel_xy, const float* __restrict__ sel_resp,
                 const int32_t* __restrict__ sel_count,

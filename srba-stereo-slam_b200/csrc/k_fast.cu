@@ -8,13 +8,12 @@
 // score is strictly greater than all 8 neighbours.  Only corners inside the border-filtered ROI
 // (runByImageBorder(edgeThreshold)) are emitted -- the others can never survive.
 //
-// One launch covers all levels and images: blockIdx.x -> (level, tile) through a prefix table,
-// blockIdx.y -> image.  A CTA stages its 136x24 pixel footprint with one 3-D TMA load, then:
+// One launch covers all levels and images: blockIdx.x -> (level, tile) through a tile table,
+// blockIdx.y -> image.  A CTA (128x32 keypoint tile) stages its 142x40 pixel footprint with one 3-D TMA load, then:
 //   A.  SWAR quick reject, 4 pixels per thread (VABSDIFF4 + byte-parallel compares) on the opposite
 //       pairs (0,8) and (4,12); survivors are compacted into a shared list (warp scan + one atomic);
-//   B1. exact FAST-9 test on the survivors: the 16 ring bytes are packed 4 per word, compared SWAR,
-//       folded to two 16-bit masks and tested for 9 contiguous bits; corners are compacted again;
-//   B2. arc score of the corners (sliding-window min/max), written to the shared score tile;
+//   B.  exact corner strength of the survivors, both polarities at once in packed s16x2 (VIMNMX.S16x2
+//       sliding-window min over the ring); corners get their score and are compacted again;
 //   C.  3x3 strict NMS evaluated only at the corners; survivors are appended to the per-(image,level)
 //       raw list with one warp-aggregated atomic per warp.
 // Integer-only; bounded by HBM reads of the level (1 byte/pixel) plus issue slots for the tests.
@@ -50,8 +49,9 @@ __device__ __forceinline__ uint32_t nibble_of_flags(uint32_t f80)               
 #define FAST_WJ 34                       // score words per row: pixel columns tx0-4 .. tx0+131
 #define FAST_NPOS (FAST_SH * FAST_WJ * 4)
 #define FAST_TP (FAST_BOX_W / 4)         // tile pitch in words
+#define FAST_AK ((FAST_SH * FAST_WJ + 255) / 256)   // score words per thread in phase A (<= 8: 4 flag bits each)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint32_t* __restrict__ raw,
             int32_t* __restrict__ raw_count, const int th)
 {
@@ -87,9 +87,9 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     //         so a corner needs |p-v| > th on (0 or 8) and on (4 or 12) -------------------------------
     const uint32_t kq = (uint32_t)(0x7f - th) * 0x01010101u;
     {
-        uint32_t m[3];
+        uint32_t m[FAST_AK];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < FAST_AK; ++k) {
             const int idx = tid + 256 * k;
             m[k] = 0;
             if (idx < FAST_SH * FAST_WJ) {
@@ -104,9 +104,11 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
                 }
             }
         }
-        // compaction: the 12 byte flags of this thread fold into a 12-bit mask; one shared atomic per thread
+        // compaction: the byte flags of this thread fold into one bit mask (4 bits per word); one shared atomic per thread
         // that has survivors (ptxas aggregates same-address atomics across the warp), then a short bit loop
-        uint32_t cm = nibble_of_flags(m[0]) | (nibble_of_flags(m[1]) << 4) | (nibble_of_flags(m[2]) << 8);
+        uint32_t cm = 0;
+#pragma unroll
+        for (int k = 0; k < FAST_AK; ++k) cm |= nibble_of_flags(m[k]) << (4 * k);
         if (cm) {
             int o = atomicAdd(&n1, __popc(cm));
             do {
@@ -118,68 +120,50 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     }
     __syncthreads();
 
-    // ---- B1: exact FAST-9 test on the survivors; the 16 ring bytes are packed 4 per word and compared SWAR ----
+    // ---- B: exact corner strength of the survivors, both polarities at once in packed s16x2 ---------------------
+    // P[k] = (ring_k - v | v - ring_k << 16); strength = max over the 16 arcs of the min over 9 contiguous P
+    // (sliding-window min by doubling: 4 x 16 VIMNMX.S16x2), corner iff max(lo, hi) > th, score = strength - 1.
     const int nc1 = n1;
     for (int base = (tid >> 5) * 32; base < nc1; base += 256) {        // warp-strided: idle warps skip the loop
         const int i = base + lane;
-        bool corner = false; uint32_t entry = 0;
+        bool corner = false; int pos = 0;
         if (i < nc1) {
-            const int pos = list1[i];
+            pos = list1[i];
             const int wi = pos >> 2, r = wi / FAST_WJ, j = wi - r * FAST_WJ;
             const uint8_t* c = tb + (r + 3) * FAST_BOX_W + 4 * j + (pos & 3);
-            const int v = c[0];
-            const uint32_t w0 = c[3 * FAST_BOX_W] | (c[3 * FAST_BOX_W + 1] << 8) | (c[2 * FAST_BOX_W + 2] << 16) | (c[FAST_BOX_W + 3] << 24);
-            const uint32_t w1 = c[3] | (c[-FAST_BOX_W + 3] << 8) | (c[-2 * FAST_BOX_W + 2] << 16) | (c[-3 * FAST_BOX_W + 1] << 24);
-            const uint32_t w2 = c[-3 * FAST_BOX_W] | (c[-3 * FAST_BOX_W - 1] << 8) | (c[-2 * FAST_BOX_W - 2] << 16) | (c[-FAST_BOX_W - 3] << 24);
-            const uint32_t w3 = c[-3] | (c[FAST_BOX_W - 3] << 8) | (c[2 * FAST_BOX_W - 2] << 16) | (c[3 * FAST_BOX_W - 1] << 24);
-            const uint32_t hi4 = (uint32_t)min(v + th, 255) * 0x01010101u, lo4 = (uint32_t)max(v - th, 0) * 0x01010101u;
-            const uint32_t mb = nibble_of_flags(gt80(w0, hi4)) | (nibble_of_flags(gt80(w1, hi4)) << 4) |
-                                (nibble_of_flags(gt80(w2, hi4)) << 8) | (nibble_of_flags(gt80(w3, hi4)) << 12);
-            const uint32_t md = nibble_of_flags(gt80(lo4, w0)) | (nibble_of_flags(gt80(lo4, w1)) << 4) |
-                                (nibble_of_flags(gt80(lo4, w2)) << 8) | (nibble_of_flags(gt80(lo4, w3)) << 12);
-            const bool isb = arc9_any(mb);
-            corner = isb || arc9_any(md);
-            entry = (uint32_t)pos | (isb ? 0x8000u : 0u);
+            const uint32_t v = c[0];
+            const uint32_t v2 = v * 0xFFFF0001u + 0x00FF0000u;          // (v | (255 - v) << 16)
+            uint32_t P[16];
+#define RINGP(k, off) P[k] = __vsub2((uint32_t)c[off] * 0xFFFF0001u + 0x00FF0000u, v2)
+            RINGP(0, 3 * FAST_BOX_W);       RINGP(1, 3 * FAST_BOX_W + 1);   RINGP(2, 2 * FAST_BOX_W + 2);   RINGP(3, FAST_BOX_W + 3);
+            RINGP(4, 3);                    RINGP(5, -FAST_BOX_W + 3);      RINGP(6, -2 * FAST_BOX_W + 2);  RINGP(7, -3 * FAST_BOX_W + 1);
+            RINGP(8, -3 * FAST_BOX_W);      RINGP(9, -3 * FAST_BOX_W - 1);  RINGP(10, -2 * FAST_BOX_W - 2); RINGP(11, -FAST_BOX_W - 3);
+            RINGP(12, -3);                  RINGP(13, FAST_BOX_W - 3);      RINGP(14, 2 * FAST_BOX_W - 2);  RINGP(15, 3 * FAST_BOX_W - 1);
+#undef RINGP
+            uint32_t m2[16], m4[16], best = 0x80008000u;               // (-32768, -32768)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m2[k] = __vmins2(P[k], P[(k + 1) & 15]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t m8 = __vmins2(m4[k], m4[(k + 4) & 15]);
+                best = __vmaxs2(best, __vmins2(m8, P[(k + 8) & 15]));
+            }
+            const int strength = max((int)(short)(best & 0xffffu), (int)(short)(best >> 16));
+            corner = strength > th;
+            if (corner) score[pos] = (uint8_t)(strength - 1);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, corner);
         if (bal) {
             int wbase = 0;
             if (lane == 0) wbase = atomicAdd(&n2, __popc(bal));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (corner) list2[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)entry;
+            if (corner) list2[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)pos;
         }
     }
     __syncthreads();
-
-    // ---- B2: corner score = (max over the 16 arcs of the min over the arc of +-(ring - centre)) - 1 -----------
     const int nc2 = n2;
-    for (int i = tid; i < nc2; i += 256) {
-        const int e16 = list2[i];
-        const int pos = e16 & 0x7fff;
-        const int wi = pos >> 2, r = wi / FAST_WJ, j = wi - r * FAST_WJ;
-        const uint8_t* c = tb + (r + 3) * FAST_BOX_W + 4 * j + (pos & 3);
-        const int v = c[0];
-        const int sg = (e16 & 0x8000) ? 1 : -1;
-        int e[16];
-        e[0] = c[3 * FAST_BOX_W];       e[1] = c[3 * FAST_BOX_W + 1];   e[2] = c[2 * FAST_BOX_W + 2];   e[3] = c[FAST_BOX_W + 3];
-        e[4] = c[3];                    e[5] = c[-FAST_BOX_W + 3];      e[6] = c[-2 * FAST_BOX_W + 2];  e[7] = c[-3 * FAST_BOX_W + 1];
-        e[8] = c[-3 * FAST_BOX_W];      e[9] = c[-3 * FAST_BOX_W - 1];  e[10] = c[-2 * FAST_BOX_W - 2]; e[11] = c[-FAST_BOX_W - 3];
-        e[12] = c[-3];                  e[13] = c[FAST_BOX_W - 3];      e[14] = c[2 * FAST_BOX_W - 2];  e[15] = c[3 * FAST_BOX_W - 1];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = sg * (e[k] - v);
-        int m2[16], m4[16], best = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) m2[k] = min(e[k], e[(k + 1) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int m8 = min(m4[k], m4[(k + 4) & 15]);
-            best = max(best, min(m8, e[(k + 8) & 15]));
-        }
-        score[pos] = (uint8_t)(best - 1);
-    }
-    __syncthreads();
 
     // ---- C: 3x3 strict NMS, only at the corners, + emit ----------------------------------------------------
     int32_t* cnt = raw_count + (size_t)img * P.nlevels + level;

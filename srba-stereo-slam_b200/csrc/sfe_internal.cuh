@@ -16,18 +16,19 @@
 #define PYR_TH 16
 #define PYR_BOX_W 176      // >= ceil(127*scale)+3 + 15 (16-byte aligned box start), multiple of 16
 #define PYR_BOX_H 24       // >= ceil(15*scale)+3
-// FAST: 128x16 keypoint tile; scores on 130x18; pixels 136x24 (+15 alignment slack) -> TMA box 160x24.
+// FAST: 128x32 keypoint tile; scores on 136x34; pixels 142x40 (+ alignment slack) -> TMA box 160x40.
 // TMA needs the box start 16-byte aligned in x: kernels round the start down and keep the offset.
 #define FAST_TW 128
-#define FAST_TH 16
+#define FAST_TH 32
 #define FAST_BOX_W 160
-#define FAST_BOX_H 24
-#define FAST_SH 18
-// Blur: 128x16 output tile, halo 3 -> 134x22 used of a 160x24 box.
+#define FAST_BOX_H 40
+#define FAST_SH (FAST_TH + 2)
+// Blur: 128x32 output tile, halo 3 -> 134x38 used of a 160x40 box.
 #define BLUR_TW 128
-#define BLUR_TH 16
+#define BLUR_TH 32
 #define BLUR_BOX_W 160
-#define BLUR_BOX_H 24       // shares the 160x24 maps with FAST (rows 22,23 unused)
+#define BLUR_BOX_H 40       // shares the 160x40 maps with FAST (rows 38,39 unused)
+#define BLUR_ROWS (BLUR_TH + 6)
 
 #define SEL_THREADS 512
 #define SEL_TIE_SLACK 64   // extra slots per level for Harris-response ties
@@ -49,7 +50,7 @@ struct LevelGeom {
 
 // Everything the all-level kernels need, passed as one __grid_constant__ parameter.
 struct alignas(64) LevelPack {
-    CUtensorMap pyr_map[SFE_MAX_LEVELS];    // 3-D (x, y, image) u8 maps over the pyramid levels, box 160x24
+    CUtensorMap pyr_map[SFE_MAX_LEVELS];    // 3-D (x, y, image) u8 maps over the pyramid levels, box 160x40
     LevelGeom g[SFE_MAX_LEVELS];
     int nlevels;
     int ftile_prefix[SFE_MAX_LEVELS + 1];   // blockIdx.x -> level for the FAST kernel
