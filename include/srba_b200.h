@@ -166,6 +166,28 @@ int sfe_match_bf_batch_device(sfe_context* ctx, const uint8_t* d_query, const in
                               const uint8_t* d_train, const int32_t* d_t_ofs, int npairs,
                               int max_nq, uint32_t* d_best);
 
+/* ---- pair-list brute force over local / peer keyframe stores ---------------------------------------------
+ * Loop-closure batches (BASELINE.json configs[3]): many (query keyframe, database keyframe) problems at once,
+ * where the database keyframe may live on ANOTHER GPU of the box.  d_train_bases is a device array of per-rank
+ * base pointers (the local one and cudaIpc-mapped peers, see sfe_ipc_*); the kernel loads peer descriptors
+ * straight through NVLink -- no all-gather of the database.  Same match semantics as sfe_match_bf.
+ * d_best (best_entries packed keys) is reset to 0xFFFFFFFF by the call; asynchronous on sfe_stream(). */
+typedef struct sfe_bf_pair {
+    int32_t q_start, nq;            /* query descriptors [q_start, q_start+nq) of d_query                     */
+    int32_t t_rank, t_start, nt;    /* train descriptors [t_start, t_start+nt) of d_train_bases[t_rank]       */
+    int32_t out_start;              /* d_best[out_start + q] receives (dist<<16 | train index within the kf)  */
+} sfe_bf_pair;
+int sfe_match_bf_pairs_device(sfe_context* ctx, const uint8_t* d_query, const uint8_t* const* d_train_bases,
+                              const sfe_bf_pair* d_pairs, int npairs, int max_nq, uint32_t* d_best, size_t best_entries);
+/* Raw device buffers that can be shared between the one-process-per-GPU ranks with CUDA IPC. */
+int sfe_device_alloc(sfe_context* ctx, size_t bytes, void** out);
+int sfe_device_free(sfe_context* ctx, void* p);
+int sfe_copy_h2d(sfe_context* ctx, void* dst, const void* src, size_t bytes);
+int sfe_copy_d2h(sfe_context* ctx, void* dst, const void* src, size_t bytes);
+int sfe_ipc_export(sfe_context* ctx, const void* dptr, uint8_t handle[64]);
+int sfe_ipc_import(sfe_context* ctx, const uint8_t handle[64], void** dptr);
+int sfe_ipc_close(sfe_context* ctx, void* dptr);
+
 /* ---- timing helpers (CUDA events on sfe_stream()) -------------------------------------------- */
 int sfe_timer_start(sfe_context* ctx);
 int sfe_timer_stop(sfe_context* ctx, float* ms);       /* synchronises on the stop event        */

@@ -11,6 +11,8 @@
 
 void sfe_upload_blur_taps(const float* taps);
 void launch_bf_init(cudaStream_t s, uint32_t* best, int n);
+void launch_bf_pairs(cudaStream_t s, const uint8_t* dq, const uint8_t* const* train_bases, const sfe_bf_pair* pairs,
+                     int npairs, int max_nq, uint32_t* best);
 
 static std::string g_create_err;
 
@@ -656,6 +658,61 @@ extern "C" int sfe_match_bf(sfe_context* c, const uint8_t* q, int nq, const uint
     *n_out = nq;
     return SFE_OK;
 }
+
+// ---- pair-list brute force over local / peer keyframe stores ---------------------------------------------------
+extern "C" int sfe_match_bf_pairs_device(sfe_context* c, const uint8_t* d_query, const uint8_t* const* d_train_bases,
+                                         const sfe_bf_pair* d_pairs, int npairs, int max_nq, uint32_t* d_best, size_t best_entries)
+{
+    if (!c || !d_query || !d_train_bases || !d_pairs || !d_best || npairs < 1 || npairs > 65535 * 16) return SFE_ERR_INVALID;
+    SFE_CUDA(c, cudaMemsetAsync(d_best, 0xff, best_entries * sizeof(uint32_t), c->stream));
+    for (int p0 = 0; p0 < npairs; p0 += 65535) {                 // gridDim.z limit
+        const int n = std::min(65535, npairs - p0);
+        launch_bf_pairs(c->stream, d_query, d_train_bases, d_pairs + p0, n, max_nq, d_best);
+        c->launches++;
+    }
+    SFE_CUDA(c, cudaGetLastError());
+    return SFE_OK;
+}
+
+// ---- raw device memory + CUDA IPC (peer-mapped keyframe stores across the one-process-per-GPU ranks) ------------
+extern "C" int sfe_device_alloc(sfe_context* c, size_t bytes, void** out)
+{
+    if (!c || !out) return SFE_ERR_INVALID;
+    SFE_CUDA(c, cudaMalloc(out, bytes));
+    return SFE_OK;
+}
+extern "C" int sfe_device_free(sfe_context* c, void* p) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaFree(p)); return SFE_OK; }
+extern "C" int sfe_copy_h2d(sfe_context* c, void* dst, const void* src, size_t bytes)
+{
+    if (!c) return SFE_ERR_INVALID;
+    SFE_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    SFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SFE_OK;
+}
+extern "C" int sfe_copy_d2h(sfe_context* c, void* dst, const void* src, size_t bytes)
+{
+    if (!c) return SFE_ERR_INVALID;
+    SFE_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SFE_OK;
+}
+extern "C" int sfe_ipc_export(sfe_context* c, const void* dptr, uint8_t handle[64])
+{
+    if (!c || !dptr || !handle) return SFE_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    SFE_CUDA(c, cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+    memcpy(handle, &h, 64);
+    return SFE_OK;
+}
+extern "C" int sfe_ipc_import(sfe_context* c, const uint8_t handle[64], void** dptr)
+{
+    if (!c || !handle || !dptr) return SFE_ERR_INVALID;
+    cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
+    SFE_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SFE_OK;
+}
+extern "C" int sfe_ipc_close(sfe_context* c, void* dptr) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaIpcCloseMemHandle(dptr)); return SFE_OK; }
 
 // ---- timing ---------------------------------------------------------------------------------------------
 extern "C" int sfe_timer_start(sfe_context* c) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaEventRecord(c->ev_start, c->stream)); return SFE_OK; }
