@@ -1,0 +1,171 @@
+#include "da_filters.h"
+#include "CBoWManager.h"
+#include <cmath>
+#include <deque>
+
+// ---- cores on plain arrays (shared by the class-level functions and the C test shims) ----------------------
+static void direction_core(const float* txy, const float* oxy, int n, float offset, int* status)
+{
+    const int N_BINS = 36, BIN_WIDTH = 10;
+    std::vector<size_t> hist(N_BINS, 0);
+    std::vector<std::deque<size_t>> hist_m(N_BINS);
+    for (int k = 0; k < n; ++k) {
+        if (status[k] != TVectorDAMatchInfo::sTRACKED) continue;
+        const float tx = txy[2 * k], ty = txy[2 * k + 1];
+        const float ox = oxy[2 * k], oy = oxy[2 * k + 1] + offset;     // 'offset' reduces the influence of location errors
+        double ang = 180 / M_PI * atanf((oy - ty) / (ox - tx)) + 180.;  // as written in the reference: atanf, not atan2
+        if (!(ang >= 0.0 && ang < 360.0)) continue;                    // NaN (coincident points): UB in the reference, skipped here
+        const size_t bin = (size_t)floor(ang / BIN_WIDTH);
+        hist[bin]++; hist_m[bin].push_back(k);
+    }
+    int mode = 0, best_so_far = 0;
+    for (size_t k = 0; k < hist.size(); ++k) if ((int)hist[k] > best_so_far) { best_so_far = (int)hist[k]; mode = (int)k; }
+    const size_t ibin_0 = mode == 0 ? N_BINS - 1 : mode - 1, ibin_1 = mode, ibin_2 = mode == N_BINS - 1 ? 0 : mode + 1;
+    for (size_t k = 0; k < (size_t)N_BINS; ++k) {
+        if (k == ibin_0 || k == ibin_1 || k == ibin_2) continue;
+        for (size_t k1 = 0; k1 < hist_m[k].size(); ++k1) status[hist_m[k][k1]] = TVectorDAMatchInfo::sREJ_SLOPE;
+    }
+}
+
+static void orb_distance_core(const int* query_idx, const int* train_idx, const float* distance, int n, int n_other, double max_dist, int* status)
+{
+    std::vector<std::pair<int, float>> other_matched(n_other, std::make_pair(-1, std::numeric_limits<float>::max()));   // t_vector_pair_idx_distance, UTL.h:509
+    size_t stage1_counter = 0;
+    for (int i = 0; i < n; ++i) {
+        const int q = query_idx[i], t = train_idx[i];
+        if (status[q] != TVectorDAMatchInfo::sTRACKED) continue;                       // rejected by a previous stage
+        if (distance[i] > max_dist) { status[q] = TVectorDAMatchInfo::sREJ_ORB; continue; }
+        if (distance[i] > other_matched[t].second) { status[q] = TVectorDAMatchInfo::sNON_TRACKED; continue; }
+        if (other_matched[t].first != -1) { status[other_matched[t].first] = TVectorDAMatchInfo::sNON_TRACKED; --stage1_counter; }
+        other_matched[t].first = q;
+        other_matched[t].second = (float)(++stage1_counter);    // the reference's bug (EST.cpp:2003-2007): the counter, not the distance
+    }
+}
+
+// ---- reference-shaped entry points ------------------------------------------------------------------------------
+void detectOutliersWithDirection(TVectorDAMatchInfo& m, const size_t& offset, const CStereoSLAMKF& this_kf, const CStereoSLAMKF& other_kf)
+{
+    const int n = (int)m.size();
+    std::vector<float> txy(2 * n), oxy(2 * n); std::vector<int> st(n);
+    for (int k = 0; k < n; ++k) {
+        st[k] = m.m_status[k];
+        if (m.m_status[k] != TVectorDAMatchInfo::sTRACKED) continue;
+        const cv::KeyPoint& a = this_kf.m_keypoints_left[this_kf.m_matches[k].queryIdx];
+        const cv::KeyPoint& b = other_kf.m_keypoints_left[other_kf.m_matches[m.m_matches[k].trainIdx].queryIdx];
+        txy[2 * k] = a.pt.x; txy[2 * k + 1] = a.pt.y; oxy[2 * k] = b.pt.x; oxy[2 * k + 1] = b.pt.y;
+    }
+    direction_core(txy.data(), oxy.data(), n, (float)offset, st.data());
+    for (int k = 0; k < n; ++k) m.m_status[k] = (TVectorDAMatchInfo::TDAMatchStatus)st[k];
+}
+
+void detectOutliersWithOrbDistance(TVectorDAMatchInfo& m, double max_orb_distance_da, const CStereoSLAMKF& this_kf, const CStereoSLAMKF& other_kf)
+{
+    const int n = (int)m.m_matches.size();
+    std::vector<int> q(n), t(n), st(m.size()); std::vector<float> d(n);
+    for (int i = 0; i < n; ++i) { q[i] = m.m_matches[i].queryIdx; t[i] = m.m_matches[i].trainIdx; d[i] = m.m_matches[i].distance; }
+    for (size_t k = 0; k < m.size(); ++k) st[k] = m.m_status[k];
+    (void)this_kf;
+    orb_distance_core(q.data(), t.data(), d.data(), n, (int)other_kf.m_matches.size(), max_orb_distance_da, st.data());
+    for (size_t k = 0; k < m.size(); ++k) m.m_status[k] = (TVectorDAMatchInfo::TDAMatchStatus)st[k];
+}
+
+void fillTrackingInfo(const TVectorDAMatchInfo& m, const CStereoSLAMKF& other_kf, t_kf_da_info& out_da)
+{
+    out_da.kf_idx = other_kf.m_kf_ID; out_da.tracked_matches = 0;
+    out_da.tracking_info.assign(m.size(), std::make_pair(INVALID_IDX, 0.0));
+    for (size_t k = 0; k < m.size(); ++k)
+        if (m.m_status[k] == TVectorDAMatchInfo::sTRACKED) {
+            out_da.tracking_info[k] = std::make_pair((size_t)m.m_matches[k].trainIdx, (double)m.m_matches[k].distance);
+            out_da.tracked_matches++;
+        }
+}
+
+void internalDataAssociation(sfe_context* ctx, const CStereoSLAMKF& this_kf, const CStereoSLAMKF& other_kf, bool by_direction, bool by_orb,
+                             double max_orb_distance_da, size_t image_rows, t_kf_da_info& out_da)
+{
+    TVectorDAMatchInfo this_matches(this_kf.m_matches.size());
+    matchKeyframes(ctx, this_kf, other_kf, this_matches.m_matches);                     // EST.cpp:1432-1452 on the GPU
+    if (this_matches.m_matches.size() != this_matches.m_status.size()) {               // empty train set: nothing tracked
+        out_da.kf_idx = other_kf.m_kf_ID; out_da.tracked_matches = 0;
+        out_da.tracking_info.assign(this_kf.m_matches.size(), std::make_pair(INVALID_IDX, 0.0));
+        return;
+    }
+    if (by_direction) detectOutliersWithDirection(this_matches, image_rows, this_kf, other_kf);
+    if (by_orb) detectOutliersWithOrbDistance(this_matches, max_orb_distance_da, this_kf, other_kf);
+    fillTrackingInfo(this_matches, other_kf, out_da);
+}
+
+std::pair<size_t, size_t> assignMatchIds(CStereoSLAMKF& new_kf, const TVectorKfsDaInfo& daInfo, const std::vector<size_t>& sorted,
+                                         const t_vector_kf& keyframes, size_t& last_match_id)
+{
+    const size_t nMatches = new_kf.m_matches.size(), numberSimilarKfs = sorted.size();
+    new_kf.m_matches_ID.assign(nMatches, 0);
+    size_t numberNewFeats = 0, numberTrackedFeats = 0;
+    std::set<size_t> foundIds;
+    for (size_t m = 0; m < nMatches; ++m) {
+        bool tracked = false;
+        for (size_t k = 0; !tracked && k < numberSimilarKfs; ++k) {
+            const t_kf_da_info& da_info = daInfo[sorted[k]];
+            if (da_info.tracking_info[m].first != INVALID_IDX) {
+                const size_t other_match_idx = da_info.tracking_info[m].first;
+                const size_t other_match_id = keyframes[da_info.kf_idx].m_matches_ID[other_match_idx];
+                if (foundIds.find(other_match_id) != foundIds.end()) break;            // "keep the first one" (EST.cpp:587-592)
+                foundIds.insert(other_match_id);
+                new_kf.m_matches_ID[m] = other_match_id;
+                numberTrackedFeats++; tracked = true;
+            }
+        }
+        if (!tracked) { new_kf.m_matches_ID[m] = ++last_match_id; numberNewFeats++; }
+    }
+    return std::make_pair(numberTrackedFeats, numberNewFeats);
+}
+
+void projectMatchTo3D(double ul, double vl, double ur, const TStereoCameraParams& c, double& X, double& Y, double& Z)
+{
+    const double b_d = c.baseline / (c.fl * (c.cur - ur) + c.fr * (ul - c.cul));
+    X = b_d * c.fr * (ul - c.cul); Y = b_d * c.fr * (vl - c.cvl); Z = b_d * c.fl * c.fr;
+}
+
+void assembleObservations(const CStereoSLAMKF& kf, const TStereoCameraParams& cam, std::vector<TObservation>& out)
+{
+    out.resize(kf.m_matches.size());
+    for (size_t i = 0; i < kf.m_matches.size(); ++i) {
+        const cv::KeyPoint& l = kf.m_keypoints_left[kf.m_matches[i].queryIdx]; const cv::KeyPoint& r = kf.m_keypoints_right[kf.m_matches[i].trainIdx];
+        TObservation& o = out[i];
+        o.feat_id = i < kf.m_matches_ID.size() ? kf.m_matches_ID[i] : i;
+        o.lx = l.pt.x; o.ly = l.pt.y; o.rx = r.pt.x; o.ry = r.pt.y;
+        projectMatchTo3D(l.pt.x, l.pt.y, r.pt.x, cam, o.X, o.Y, o.Z);
+    }
+}
+
+// ---- C shims for the CPU test-suite (ctypes) -----------------------------------------------------------------------
+extern "C" {
+void srba_da_filter_direction(const float* this_xy, const float* other_xy, int n, float offset, int* status)
+{ direction_core(this_xy, other_xy, n, offset, status); }
+void srba_da_filter_orb_distance(const int* query_idx, const int* train_idx, const float* distance, int n, int n_other, double max_dist, int* status)
+{ orb_distance_core(query_idx, train_idx, distance, n, n_other, max_dist, status); }
+void srba_project_match_to_3d(double ul, double vl, double ur, const double* cam6, double* xyz)
+{ TStereoCameraParams c = { cam6[0], cam6[1], cam6[2], cam6[3], cam6[4], cam6[5] }; projectMatchTo3D(ul, vl, ur, c, xyz[0], xyz[1], xyz[2]); }
+// ids: tracking_first [nkf][nmatches] (int64, -1 = INVALID), kf_ids [nkf], per-kf id arrays flattened with offsets
+void srba_da_assign_ids(int nmatches, int nkf, const long long* tracking_first, const int* da_kf_idx, const int* sorted,
+                        const long long* kf_ids_flat, const int* kf_ids_ofs, int n_keyframes, long long* last_match_id, long long* out_ids,
+                        long long* n_tracked, long long* n_new)
+{
+    t_vector_kf kfs(n_keyframes);
+    for (int k = 0; k < n_keyframes; ++k) for (int i = kf_ids_ofs[k]; i < kf_ids_ofs[k + 1]; ++i) kfs[k].m_matches_ID.push_back((size_t)kf_ids_flat[i]);
+    TVectorKfsDaInfo da(nkf);
+    for (int k = 0; k < nkf; ++k) {
+        da[k].kf_idx = (size_t)da_kf_idx[k]; da[k].tracking_info.resize(nmatches);
+        for (int m = 0; m < nmatches; ++m) {
+            const long long f = tracking_first[(size_t)k * nmatches + m];
+            da[k].tracking_info[m] = std::make_pair(f < 0 ? INVALID_IDX : (size_t)f, 0.0);
+        }
+    }
+    CStereoSLAMKF nk; nk.m_matches.resize(nmatches);
+    std::vector<size_t> srt(sorted, sorted + nkf);
+    size_t last = (size_t)*last_match_id;
+    const std::pair<size_t, size_t> r = assignMatchIds(nk, da, srt, kfs, last);
+    for (int m = 0; m < nmatches; ++m) out_ids[m] = (long long)nk.m_matches_ID[m];
+    *last_match_id = (long long)last; *n_tracked = (long long)r.first; *n_new = (long long)r.second;
+}
+}
