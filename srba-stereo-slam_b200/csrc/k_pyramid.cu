@@ -6,7 +6,7 @@
 // int32, vertical pass (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.  The coefficient tables
 // are computed on the host exactly as OpenCV does (double/float) so the kernel is pure integer.
 //
-// One CTA = one 128x16 destination tile of one image.  Its source footprint (<= 176x24 u8 incl. alignment slack) is
+// One CTA = one 128x32 destination tile of one image.  Its source footprint (<= 176x48 u8 incl. alignment slack) is
 // fetched with a single 3-D TMA load (out-of-bounds rows/columns arrive as zeros and are never
 // weighted).  The horizontal pass runs once per SOURCE row on word loads: a funnel shift aligns the
 // footprint of 4 destination columns, two PRMTs gather the (left,right) byte pairs and DP2A applies the
@@ -48,15 +48,18 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     const uint32_t sel = __ldg(ge + 1);
     const uint32_t c0 = __ldg(ge + 2), c1 = __ldg(ge + 3), c2 = __ldg(ge + 4), c3 = __ldg(ge + 5);
     const int wi = off >> 2, sh = (off & 3) * 8;
-    int2 yt[2];
+    int2 yt[PYR_TH / 8];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) yt[k] = a.ytab[min(y0 + rr + 8 * k, a.dh - 1)];
+    for (int k = 0; k < PYR_TH / 8; ++k) yt[k] = a.ytab[min(y0 + rr + 8 * k, a.dh - 1)];
+    // source rows this tile really needs: [sy0, last row of the last destination row + 1]
+    const int nrows = min(a.ytab[min(y0 + PYR_TH, a.dh) - 1].x + 1, a.sh - 1) - sy0 + 1;
     mbar_wait(&bar, 0);
 
     // ---- horizontal pass, once per source row: h = S[sx]*a0 + S[sx+1]*a1 (DP2A), stored as (h >> 4) in u16 ----
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < PYR_BOX_H / 8; ++k) {
         const int r = rr + 8 * k;
+        if (r >= nrows) break;
         const uint32_t* row = tile + r * PYR_TPW + wi;
         const uint32_t A = __funnelshift_r(row[0], row[1], sh), B = __funnelshift_r(row[1], row[2], sh);
         const uint32_t b01 = __byte_perm(A, B, sel & 0xffffu), b23 = __byte_perm(A, B, sel >> 16);
@@ -68,7 +71,7 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
 
     // ---- vertical pass: (((b0*r0) >> 16) + ((b1*r1) >> 16) + 2) >> 2, 4 pixels per 32-bit store --------------
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < PYR_TH / 8; ++k) {
         const int dy = y0 + rr + 8 * k;
         if (dy >= a.dh) break;
         const int r0 = min(max(yt[k].x, 0), a.sh - 1) - sy0;

@@ -11,11 +11,11 @@
 #define SFE_MAX_LEVELS 8
 
 // ---- tile geometry shared by host and device -------------------------------------------------
-// Pyramid: 128x16 output tile, source box fetched by one TMA load.
+// Pyramid: 128x32 output tile, source box fetched by one TMA load.
 #define PYR_TW 128
-#define PYR_TH 16
+#define PYR_TH 32
 #define PYR_BOX_W 176      // >= ceil(127*scale)+3 + 15 (16-byte aligned box start), multiple of 16
-#define PYR_BOX_H 24       // >= ceil(15*scale)+3
+#define PYR_BOX_H 48       // >= ceil(31*scale)+3
 // FAST: 128x32 keypoint tile; scores on 136x34; pixels 142x40 (+ alignment slack) -> TMA box 160x40.
 // TMA needs the box start 16-byte aligned in x: kernels round the start down and keep the offset.
 #define FAST_TW 128
@@ -114,7 +114,7 @@ struct sfe_context {
     uint32_t* d_gtab[SFE_MAX_LEVELS] = {};
     int4* d_ftile_tab = nullptr;             // FAST tile -> {level, tx0, ty0, 0}
     int4* d_btile_tab = nullptr;             // blur tile -> {level, x0, y0, 0}   // per 4 destination columns: {src base, PRMT selectors, 4 coefficient pairs}
-    CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 176x24-box maps over the same levels, source side of the pyramid kernel
+    CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 176x48-box maps over the same levels, source side of the pyramid kernel
     int NI = 0;                              // images the arenas are sized for (2*max_pairs)
     int sel_cand_cap = 0;                    // select kernel: shared candidate list capacity
     bool select_attr_set = false;
