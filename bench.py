@@ -314,8 +314,15 @@ def main():
     per_launch_bytes = stages[dom]["algorithmic_bytes"] / max(stages[dom]["launches"], 1)
     per_launch_ms = stages[dom]["ms"] / max(stages[dom]["launches"], 1)
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture, scaled to this batch size
+        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["traffic_bytes_per_launch"][dom] * B / tj["pairs_per_launch"] / max(stages[dom]["launches"], 1)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                "frac": achieved / peak, "traffic": traffic, "bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                 "stages": stages}
 
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) ---------------------------------------------------
