@@ -29,9 +29,16 @@ import numpy as np
 
 W, H, NFEAT, NLEVELS = 1241, 376, 1000, 8
 METRIC = "stereo frames/sec (1241x376, 1000 ORB, 8 levels, extract L+R + L/R row-band match)"
+WORKLOAD = "configs[1]: 1241x376 stereo, 1000 ORB, 8 levels, L/R row-band match"
+CONFIGS = {   # BASELINE.json configs; "b" is the headline (configs[1])
+    "a": (1226, 370, 500, 1, "configs[0]: kitti.ini as shipped, 1226x370, 500 ORB, n_levels=1, L/R row-band match"),
+    "b": (1241, 376, 1000, 8, WORKLOAD),
+    "e": (1920, 1080, 4000, 8, "configs[4]: 1920x1080 stereo, 4000 ORB, 8 levels"),
+}
 
 
-def level_pixels(w=W, h=H, nlevels=NLEVELS):
+def level_pixels(w=None, h=None, nlevels=None):
+    w, h, nlevels = w or W, h or H, nlevels or NLEVELS
     # same arithmetic as cv::ORB (float 1.2^l, cvRound) -- sizes for the algorithmic-bytes table
     px = []
     for l in range(nlevels):
@@ -40,7 +47,8 @@ def level_pixels(w=W, h=H, nlevels=NLEVELS):
     return px
 
 
-def algorithmic_bytes_per_image(nkp=NFEAT):
+def algorithmic_bytes_per_image(nkp=None):
+    nkp = nkp or NFEAT
     """SURVEY.md 8(d): unfused-minimum HBM bytes per image for each stage."""
     px = level_pixels()
     P, A0 = sum(px), px[0]
@@ -84,6 +92,28 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore its pinned staging buffers, first-touch) to the NUMA node the GPU hangs off:
+    with one rank per GPU all ranks otherwise fight over one socket's memory controllers for their H2D traffic."""
+    try:
+        bdf = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], text=True).strip().lower()
+        bdf = bdf[-12:] if len(bdf) > 12 else bdf                     # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def cpu_port_throughput(frames, threads, seconds_budget=20.0):
     """Oracle (CPU port of the reference path) on a bounded sample: extract L+R + row-band match per pair."""
     from concurrent.futures import ThreadPoolExecutor
@@ -122,7 +152,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "stereo frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1241x376 stereo, 1000 ORB, 8 levels, L/R row-band match", "pairs_per_step": n_tot // max(args.steps, 1)},
+            "config": {"workload": WORKLOAD, "pairs_per_step": n_tot // max(args.steps, 1)},
             "cpu_baseline": {"value": value, "unit": "stereo frames/s", "cores": cores, "kind": "port",
                              "sample": "%d stereo pairs over %d steps on %d host threads (oracle/frontend_oracle.c; the reference's OpenCV-2.4/stereo-vo path cannot be built here)" % (n_tot, args.steps, cores)},
             "e2e": {"value": value, "unit": "stereo frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -137,15 +167,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="b", choices=sorted(CONFIGS), help="BASELINE.json workload (default: the headline configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the full front-end (BoW + KF match) measurement")
     args = ap.parse_args()
+    global W, H, NFEAT, NLEVELS, METRIC, WORKLOAD
+    W, H, NFEAT, NLEVELS, WORKLOAD = CONFIGS[args.config]
+    METRIC = "stereo frames/sec (%dx%d, %d ORB, %d levels, extract L+R + L/R row-band match)" % (W, H, NFEAT, NLEVELS)
+    if args.config == "e":
+        args.pairs = min(args.pairs, 32)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local)
     import torch
     dist = None
     if world > 1:
@@ -233,7 +270,7 @@ def main():
     # ---- full front-end (BASELINE.json configs[2] shape): + BoW query/add + keyframe store + association -----
     full = None
     voc_path = os.path.join(ROOT, "tests", "golden", "voc_flat.npz")
-    if os.path.exists(voc_path) and not args.no_full:
+    if os.path.exists(voc_path) and not args.no_full and args.config == "b":
         vz = np.load(voc_path)
         voc = {k: (vz[k] if vz[k].ndim else vz[k].item()) for k in vz.files}
         bow = frontend.BowDatabase(fe, voc)
@@ -316,6 +353,8 @@ def main():
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     try:    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture, scaled to this batch size
+        if args.config != "b":
+            raise KeyError("traffic was captured for the headline config only")
         with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
             tj = json.load(f)
         traffic = tj["traffic_bytes_per_launch"][dom] * B / tj["pairs_per_launch"] / max(stages[dom]["launches"], 1)
@@ -336,10 +375,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "stereo frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": "configs[1]: 1241x376 stereo, 1000 ORB, 8 levels, L/R row-band match", "pairs_per_step_per_gpu": B,
+                "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B,
                            "keypoints_left_right_matches_pair0": feats,
-                           "l2": "per-step working set %.0f MB (pyramid + blurred arenas of %d images) exceeds the 126 MB L2" % (2 * nimg * 1.55, nimg),
-                           "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world},
+                           "l2": "per-step working set %.0f MB (pyramid + blurred arenas of %d images) exceeds the 126 MB L2" % (2 * nimg * sum(level_pixels()) * 1.07 / 1e6, nimg),
+                           "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world, "rank0_numa_binding": numa},
                 "e2e": {"value": e2e, "unit": "stereo frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "matches_read_back": nmatch,
                         "h2d_link_GBps_measured": h2d_gbs,

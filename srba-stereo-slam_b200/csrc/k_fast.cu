@@ -19,27 +19,10 @@
 // Integer-only; bounded by HBM reads of the level (1 byte/pixel) plus issue slots for the tests.
 #include "sfe_internal.cuh"
 
-__device__ __forceinline__ int arc9_any(uint32_t m)      // m: 16-bit ring mask; any 9 contiguous set bits (circular)?
-{
-    m |= m << 16;
-    uint32_t x = m & (m >> 1);      // runs of 2
-    x &= x >> 2;                    // runs of 4
-    x &= x >> 4;                    // runs of 8
-    x &= m >> 8;                    // runs of 9
-    return (x & 0xffffu) != 0;
-}
-
 // SWAR helpers on 4 packed bytes; flags are returned in bit 7 of each byte.
 __device__ __forceinline__ uint32_t gt80_const(uint32_t x, uint32_t k7f_minus_t)   // x > t per byte, t < 128
 {
     return (((x & 0x7f7f7f7fu) + k7f_minus_t) | x) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t gt80(uint32_t a, uint32_t b)                   // a > b per byte (unsigned)
-{
-    // ge(b,a): low 7 bits compare through a borrow-free subtract, then the top bits decide
-    const uint32_t t = (b | 0x80808080u) - (a & 0x7f7f7f7fu);
-    const uint32_t ge = (b & ~a) | (~(a ^ b) & t);
-    return ~ge & 0x80808080u;
 }
 __device__ __forceinline__ uint32_t nibble_of_flags(uint32_t f80)                  // bit 7 of byte i -> bit i
 {

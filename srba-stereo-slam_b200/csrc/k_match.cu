@@ -14,6 +14,7 @@
 // argmin with the lowest-index tie rule is a plain unsigned min (warp shuffles / atomicMin).
 // Tensor cores are deliberately not used (BASELINE.json north_star).
 #include "sfe_internal.cuh"
+#include <algorithm>
 
 __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1)
 {
@@ -22,33 +23,33 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row-band match: one CTA per stereo pair.
+// Row-band match.  Kernel 1: grid (slices, pairs) -- every CTA buckets the right keypoints of its pair by
+// image row in shared memory (counting sort, parallel scan) and matches its slice of the left keypoints,
+// one warp per left keypoint over the +-max_y_diff band.  Kernel 2: one CTA per pair, ordered compaction
+// (+ the mutual-best check) into the cv::DMatch list.
 // ------------------------------------------------------------------------------------------------
-#define RB_THREADS 512
-#define RB_MAX_ROWS 4096
+#define RB_THREADS 256
 
 struct RowBandArgs {
     const sfe_keypoint* kps; const uint8_t* desc; const int32_t* kp_count;
     sfe_dmatch* matches; int32_t* match_count;
-    int kp_cap, height;
+    uint32_t* best; uint32_t* owner;           // [pairs][kp_cap] packed (dist<<16 | idx) / (dist<<16 | left idx)
+    int kp_cap, height, slices;
     float max_y_diff, min_disp, max_disp;
     int max_dist, robust;
 };
 
 __global__ void __launch_bounds__(RB_THREADS)
-rowband_kernel(const RowBandArgs a)
+rowband_match_kernel(const RowBandArgs a)
 {
     extern __shared__ uint32_t dynm[];
-    // layout: row_start[height+2] | sorted[kp_cap] | best[kp_cap] | owner[kp_cap]
+    // layout: row_start[height+2] | sorted[kp_cap]
     int* row_start = reinterpret_cast<int*>(dynm);
     int* sorted = row_start + a.height + 2;
-    uint32_t* best = reinterpret_cast<uint32_t*>(sorted + a.kp_cap);
-    uint32_t* owner = best + a.kp_cap;
-    __shared__ int s_scan[RB_THREADS / 32];
-    __shared__ int s_total;
+    __shared__ int s_warp[RB_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pair = blockIdx.x;
+    const int pair = blockIdx.y;
     const int il = 2 * pair, ir = 2 * pair + 1;
     const int nl = min(a.kp_count[il], a.kp_cap), nr = min(a.kp_count[ir], a.kp_cap);
     const sfe_keypoint* kl = a.kps + (size_t)il * a.kp_cap;
@@ -56,22 +57,35 @@ rowband_kernel(const RowBandArgs a)
     const uint4* dl = reinterpret_cast<const uint4*>(a.desc + (size_t)il * a.kp_cap * 32);
     const uint4* dr = reinterpret_cast<const uint4*>(a.desc + (size_t)ir * a.kp_cap * 32);
     const int H = a.height;
+    const int chunk = (nl + a.slices - 1) / a.slices;
+    const int i0 = blockIdx.x * chunk, i1 = min(nl, i0 + chunk);
+    if (i0 >= i1) return;
 
     // ---- bucket the right keypoints by image row (counting sort) ----------------------------
     for (int i = tid; i < H + 2; i += RB_THREADS) row_start[i] = 0;
-    for (int i = tid; i < a.kp_cap; i += RB_THREADS) owner[i] = 0xffffffffu;
     __syncthreads();
     for (int j = tid; j < nr; j += RB_THREADS) {
         const int r = min(max((int)floorf(kr[j].y), 0), H - 1);
         atomicAdd(&row_start[r + 2], 1);
     }
     __syncthreads();
-    if (tid == 0) {                         // H <= 4096: a serial scan is a few microseconds
-        int acc = 0;
-        for (int r = 0; r < H; ++r) { acc += row_start[r + 2]; row_start[r + 2] = acc; }
-        // row_start[r+1] is now (after the scatter below) the begin of row r; row_start[r+2] its end
+    {   // inclusive scan of row_start[2 .. H+1] in place: per-thread segments + warp/block scan of the segment sums
+        const int seg = (H + RB_THREADS - 1) / RB_THREADS;
+        const int b = 2 + tid * seg, e = min(b + seg, H + 2);
+        int sum = 0;
+        for (int r = b; r < e; ++r) sum += row_start[r];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wofs = 0;
+        for (int w = 0; w < warp; ++w) wofs += s_warp[w];
+        int run = wofs + incl - sum;
+        for (int r = b; r < e; ++r) { run += row_start[r]; row_start[r] = run; }
     }
     __syncthreads();
+    // row_start[r+1] = begin of row r (after the scatter below: its end = begin of row r+1)
     for (int j = tid; j < nr; j += RB_THREADS) {
         const int r = min(max((int)floorf(kr[j].y), 0), H - 1);
         const int p = atomicAdd(&row_start[r + 1], 1);
@@ -80,8 +94,10 @@ rowband_kernel(const RowBandArgs a)
     __syncthreads();
     // now row r occupies sorted[row_start[r] .. row_start[r+1])
 
-    // ---- one warp per left keypoint ------------------------------------------------------------
-    for (int i = warp; i < nl; i += RB_THREADS / 32) {
+    // ---- one warp per left keypoint of this slice ------------------------------------------------
+    uint32_t* best = a.best + (size_t)pair * a.kp_cap;
+    uint32_t* owner = a.owner + (size_t)pair * a.kp_cap;
+    for (int i = i0 + warp; i < i1; i += RB_THREADS / 32) {
         const float xl = kl[i].x, yl = kl[i].y;
         const uint4 q0 = __ldg(dl + 2 * i), q1 = __ldg(dl + 2 * i + 1);
         const int rlo = min(max((int)floorf(yl - a.max_y_diff), 0), H - 1);
@@ -104,9 +120,18 @@ rowband_kernel(const RowBandArgs a)
             if (a.robust && key != 0xffffffffu) atomicMin(&owner[key & 0xffffu], (key & 0xffff0000u) | (uint32_t)i);
         }
     }
-    __syncthreads();
+}
 
-    // ---- ordered compaction -----------------------------------------------------------------------
+__global__ void __launch_bounds__(RB_THREADS)
+rowband_compact_kernel(const RowBandArgs a)
+{
+    __shared__ int s_scan[RB_THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pair = blockIdx.x;
+    const int nl = min(a.kp_count[2 * pair], a.kp_cap);
+    const uint32_t* best = a.best + (size_t)pair * a.kp_cap;
+    const uint32_t* owner = a.owner + (size_t)pair * a.kp_cap;
     sfe_dmatch* out = a.matches + (size_t)pair * a.kp_cap;
     if (tid == 0) s_total = 0;
     __syncthreads();
@@ -137,12 +162,12 @@ rowband_kernel(const RowBandArgs a)
 
 static size_t rowband_smem(const sfe_context* c)
 {
-    return sizeof(int) * ((size_t)c->cfg.height + 2 + 3 * (size_t)c->pack.kp_cap);
+    return sizeof(int) * ((size_t)c->cfg.height + 2 + (size_t)c->pack.kp_cap);
 }
 
 void prepare_rowband(sfe_context* c)
 {
-    cudaFuncSetAttribute(rowband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowband_smem(c));
+    cudaFuncSetAttribute(rowband_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowband_smem(c));
 }
 
 void launch_match_rowband(sfe_context* c, int npairs)
@@ -150,12 +175,16 @@ void launch_match_rowband(sfe_context* c, int npairs)
     RowBandArgs a;
     a.kps = c->d_kp; a.desc = c->d_desc; a.kp_count = c->d_kp_count;
     a.matches = c->d_matches; a.match_count = c->d_match_count;
+    a.best = c->d_rb_best; a.owner = c->d_rb_owner;
     a.kp_cap = c->pack.kp_cap; a.height = c->cfg.height;
     a.max_y_diff = c->cfg.max_y_diff; a.min_disp = c->cfg.min_disparity; a.max_disp = c->cfg.max_disparity;
     a.max_dist = c->orb_th; a.robust = c->cfg.robust_1to1;
-    const size_t smem = rowband_smem(c);
-    rowband_kernel<<<npairs, RB_THREADS, smem, c->stream>>>(a);
-    c->launches++;
+    // enough CTAs to fill the GPU (2 waves of 148 SMs) however small the batch, at least 64 left keypoints per slice
+    a.slices = std::max(1, std::min({ (296 + npairs - 1) / npairs, (c->cfg.nfeatures + 63) / 64, 32 }));
+    if (a.robust) cudaMemsetAsync(c->d_rb_owner, 0xff, sizeof(uint32_t) * (size_t)npairs * a.kp_cap, c->stream);
+    rowband_match_kernel<<<dim3(a.slices, npairs), RB_THREADS, rowband_smem(c), c->stream>>>(a);
+    rowband_compact_kernel<<<npairs, RB_THREADS, 0, c->stream>>>(a);
+    c->launches += 2;
 }
 
 // ------------------------------------------------------------------------------------------------

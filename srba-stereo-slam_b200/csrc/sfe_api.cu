@@ -162,6 +162,8 @@ static int create_impl(sfe_context* c)
     SFE_CUDA(c, dalloc(&c->d_kp_count, (size_t)NI));
     SFE_CUDA(c, dalloc(&c->d_matches, (size_t)f.max_pairs * P.kp_cap));
     SFE_CUDA(c, dalloc(&c->d_match_count, (size_t)f.max_pairs));
+    SFE_CUDA(c, dalloc(&c->d_rb_best, (size_t)f.max_pairs * P.kp_cap));
+    SFE_CUDA(c, dalloc(&c->d_rb_owner, (size_t)f.max_pairs * P.kp_cap));
     SFE_CUDA(c, dalloc(&c->d_status, (size_t)NI));
     SFE_CUDA(c, cudaMemset(c->d_status, 0, sizeof(int32_t) * NI));
     SFE_CUDA(c, cudaMemset(c->d_kp_count, 0, sizeof(int32_t) * NI));
@@ -212,9 +214,7 @@ static int create_impl(sfe_context* c)
             SFE_CUDA(c, dalloc(&c->d_gtab[l], gt.size()));
             SFE_CUDA(c, cudaMemcpy(c->d_gtab[l], gt.data(), gt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
-        SFE_CUDA(c, dalloc(&c->d_xtab[l], c->xtab[l].size()));
         SFE_CUDA(c, dalloc(&c->d_ytab[l], c->ytab[l].size()));
-        SFE_CUDA(c, cudaMemcpy(c->d_xtab[l], c->xtab[l].data(), c->xtab[l].size() * sizeof(int2), cudaMemcpyHostToDevice));
         SFE_CUDA(c, cudaMemcpy(c->d_ytab[l], c->ytab[l].data(), c->ytab[l].size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
 
@@ -261,7 +261,7 @@ static int create_impl(sfe_context* c)
         sfe_upload_blur_taps(k);
     }
     c->graphs.assign(f.max_pairs + 1, nullptr);
-    if ((size_t)c->sel_cand_cap * 8 > 200 * 1024 || sizeof(int) * ((size_t)f.height + 2 + 3 * (size_t)P.kp_cap) > 200 * 1024) {
+    if ((size_t)c->sel_cand_cap * 8 > 200 * 1024 || sizeof(int) * ((size_t)f.height + 2 + (size_t)P.kp_cap) > 200 * 1024) {
         c->err = "configuration needs more than 200 KB of shared memory per CTA"; return SFE_ERR_INVALID;
     }
     prepare_select(c);
@@ -289,9 +289,9 @@ extern "C" void sfe_destroy(sfe_context* c)
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
     cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_raw); cudaFree(c->d_raw_count);
     cudaFree(c->d_sel_xy); cudaFree(c->d_sel_resp); cudaFree(c->d_sel_count); cudaFree(c->d_kp); cudaFree(c->d_desc);
-    cudaFree(c->d_kp_count); cudaFree(c->d_matches); cudaFree(c->d_match_count); cudaFree(c->d_status);
+    cudaFree(c->d_rb_best); cudaFree(c->d_rb_owner); cudaFree(c->d_kp_count); cudaFree(c->d_matches); cudaFree(c->d_match_count); cudaFree(c->d_status);
     cudaFree(c->d_packed); cudaFree(c->d_ftile_tab); cudaFree(c->d_btile_tab); cudaFree(c->d_bf_q); cudaFree(c->d_bf_t); cudaFree(c->d_bf_best); cudaFree(c->d_bf_ofs);
-    for (int l = 0; l < SFE_MAX_LEVELS; ++l) { cudaFree(c->d_xtab[l]); cudaFree(c->d_ytab[l]); cudaFree(c->d_gtab[l]); }
+    for (int l = 0; l < SFE_MAX_LEVELS; ++l) { cudaFree(c->d_ytab[l]); cudaFree(c->d_gtab[l]); }
     cudaFreeHost(c->h_images); cudaFreeHost(c->h_kp); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_matches);
     cudaFreeHost(c->h_kp_count); cudaFreeHost(c->h_match_count); cudaFreeHost(c->h_status); cudaFreeHost(c->h_counts);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -736,7 +736,7 @@ extern "C" int sfe_stage_times(sfe_context* c, float* ms, int32_t* launches)
     if (!c || !ms) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
     const int L = c->pack.nlevels;
-    const int nl[ST_COUNT] = { 0, L - 1, 1, 1, 1, 1, 1, 0 };
+    const int nl[ST_COUNT] = { 0, L - 1, 1, 1, 1, 1, 2, 0 };
     for (int s = 0; s < ST_COUNT; ++s) {
         ms[s] = 0.f;
         if (s == ST_H2D || s == ST_D2H) { if (cudaEventElapsedTime(&ms[s], c->ev_stage[s], c->ev_stage[s + 1]) != cudaSuccess) { ms[s] = 0.f; cudaGetLastError(); } }

@@ -108,8 +108,7 @@ struct sfe_context {
     cudaStream_t stream = nullptr;
     std::string err;
     LevelPack pack;                          // host copy (passed by value at launch)
-    std::vector<std::vector<int2>> xtab, ytab;   // host resize tables (kept for debugging)
-    int2* d_xtab[SFE_MAX_LEVELS] = {};       // per destination level: {src offset, a0 | a1<<16}
+    std::vector<std::vector<int2>> xtab, ytab;   // host resize tables: {src offset, a0 | a1<<16} per destination column / row
     int2* d_ytab[SFE_MAX_LEVELS] = {};
     uint32_t* d_gtab[SFE_MAX_LEVELS] = {};
     int4* d_ftile_tab = nullptr;             // FAST tile -> {level, tx0, ty0, 0}
@@ -131,6 +130,8 @@ struct sfe_context {
     int32_t* d_kp_count = nullptr;           // [NI]
     sfe_dmatch* d_matches = nullptr;         // [max_pairs][kp_cap]
     int32_t* d_match_count = nullptr;        // [max_pairs]
+    uint32_t* d_rb_best = nullptr;           // [max_pairs][kp_cap] row-band match: packed best key per left keypoint
+    uint32_t* d_rb_owner = nullptr;          // [max_pairs][kp_cap] mutual-best owner per right keypoint
     int32_t* d_status = nullptr;             // [NI] device-side error flags (capacity overflow)
     // pinned staging
     uint8_t* h_images = nullptr; size_t h_images_bytes = 0;

@@ -227,3 +227,42 @@ def test_capacity_and_larger_config(mods, scene_frames):
         assert np.array_equal(m["trainIdx"], om["trainIdx"]) and np.array_equal(m["queryIdx"], om["queryIdx"])
     finally:
         fe.close()
+
+
+def test_full_batch_properties(mods, scene_frames):
+    """BASELINE.json configs[1] at the benchmark's batch size (128 pairs resident): size-independent properties --
+    determinism (idempotent re-run), replica consistency (tiled copies of a frame give identical results), canonical
+    ordering, match constraints, and the self-match identity of the brute-force matcher."""
+    frontend, orc = mods
+    B = 128
+    base = scene_frames(2)
+    frames = np.ascontiguousarray(np.tile(base, (B // 2, 1, 1, 1)))
+    fe = frontend.StereoFrontEnd(max_pairs=B)
+    try:
+        fe.upload(frames)
+        fe.process_device(B); fe.synchronize()
+        first = [fe.get_values(p) for p in (0, 1, 64, 65, 126, 127)]
+        fe.process_device(B); fe.synchronize()                      # idempotence
+        again = [fe.get_values(p) for p in (0, 1, 64, 65, 126, 127)]
+        for a, b in zip(first, again):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        for i in (2, 4):                                            # replicas of pair 0 / pair 1
+            for x, y in zip(first[0], first[i]):
+                assert np.array_equal(x, y)
+            for x, y in zip(first[1], first[i + 1]):
+                assert np.array_equal(x, y)
+        kl, kr, dl, dr, m = first[0]
+        ol, odl, _ = orc.orb_extract(base[0, 0])
+        assert np.array_equal(kl["x"], ol["x"]) and np.array_equal(dl, odl)      # and still the oracle's answer
+        for k in (kl, kr):                                           # canonical order: octave, then y, then x (level coords)
+            s = 1.2 ** k["octave"].astype(np.float64)
+            key = k["octave"].astype(np.int64) * 10**8 + np.rint(k["y"] / s).astype(np.int64) * 10**4 + np.rint(k["x"] / s).astype(np.int64)
+            assert np.all(np.diff(key) > 0)
+        assert np.all(np.diff(m["queryIdx"]) > 0) and np.all(m["distance"] <= 60) and np.all(m["imgIdx"] == 0)
+        assert np.all(np.abs(kl["y"][m["queryIdx"]] - kr["y"][m["trainIdx"]]) <= 2.0)
+        assert np.all(kl["x"][m["queryIdx"]] - kr["x"][m["trainIdx"]] >= 0.0)
+        self_m = fe.match_bf(dl, dl)                                 # identity, unless two descriptors coincide
+        assert np.all(self_m["distance"] == 0) and np.all(self_m["trainIdx"] <= self_m["queryIdx"])
+    finally:
+        fe.close()
