@@ -52,6 +52,10 @@ typedef struct sfe_dmatch {
 enum { SFE_BLUR_CV24_FIXED = 0,   /* OpenCV-2.4 8-bit fixed-point Gaussian (reference parity)     */
        SFE_BLUR_FLOAT = 1 };      /* float sepFilter2D arithmetic (OpenCV >= 3.4; cv2-pinned)     */
 
+enum { SFE_PYRAMID_CV24_LINEAR = 0,  /* OpenCV-2.4 resize(INTER_LINEAR), 11-bit coefficients (reference parity)   */
+       SFE_PYRAMID_CV4_EXACT = 1 };  /* INTER_LINEAR_EXACT + cv>=3 level sizes; with SFE_BLUR_FLOAT the whole
+                                        extraction is bit-identical to cv2 4.13's ORB (pinned by tests/golden)    */
+
 typedef struct sfe_config {
     int32_t width, height;      /* level-0 image size ([CAMERA_LEFT] ncols/nrows, kitti.ini:139,147) */
     int32_t nlevels;            /* params_detect.orb_nlevels, EST.cpp:1141 (1..8)                  */
@@ -68,6 +72,7 @@ typedef struct sfe_config {
     int32_t robust_1to1;        /* [MATCH] enable_robust_1to1_match, kitti.ini:18                  */
     int32_t device;             /* CUDA device ordinal                                             */
     int32_t use_graph;          /* 1: replay the batch as a CUDA graph                             */
+    int32_t pyramid_mode;       /* SFE_PYRAMID_*                                                   */
 } sfe_config;
 
 void sfe_default_config(sfe_config* cfg);   /* kitti.ini values, 1241x376, 8 levels, 1000 feats */

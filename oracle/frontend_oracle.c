@@ -62,6 +62,17 @@ void orc_level_sizes(int W, int H, int nlevels, float scale_factor, int32_t* lw,
     }
 }
 
+/* OpenCV >= 3.x writes Size(cvRound(cols/scale), cvRound(rows/scale)) -- a float division instead of a multiplication
+ * by the reciprocal; same sizes for every configuration in BASELINE.json, kept separate for exactness. */
+void orc_level_sizes_cv4(int W, int H, int nlevels, float scale_factor, int32_t* lw, int32_t* lh)
+{
+    for (int l = 0; l < nlevels; ++l) {
+        float scale = orc_level_scale(l, scale_factor);
+        lw[l] = cv_round((double)((float)W / scale));
+        lh[l] = cv_round((double)((float)H / scale));
+    }
+}
+
 void orc_level_quotas(int nfeatures, int nlevels, float scale_factor, int32_t* quota)
 {
     float factor = (float)(1.0 / (double)scale_factor);
@@ -126,6 +137,42 @@ void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
             D[dx] = (uint8_t)((((b0 * (r0[dx] >> 4)) >> 16) + ((b1 * (r1[dx] >> 4)) >> 16) + 2) >> 2);
     }
     free(xofs); free(ia); free(yofs); free(ib); free(r0); free(r1);
+}
+
+/* 8-bit INTER_LINEAR_EXACT (pyramid_mode 1): the bit-exact resize OpenCV >= 3.4 uses for ORB's pyramid.
+ * Coefficients are 8-bit fractions round((f - floor f) * 256) from f = (1/(dst/src)) * (d + 0.5) - 0.5 in double;
+ * horizontal pass h = c0*p0 + c1*p1 (8.8 fixed point, exact), vertical pass (b0*h0 + b1*h1 + 2^15) >> 16;
+ * outside the source the nearest edge sample is taken with full weight.  Pinned bit-exactly against
+ * cv2.resize(INTER_LINEAR_EXACT). */
+static void exact_coeffs(int ssize, int dsize, int32_t* ofs, int32_t* c1)
+{
+    double inv = (double)dsize / ssize, scale = 1.0 / inv;
+    for (int v = 0; v < dsize; ++v) {
+        double f = scale * ((double)v + 0.5) - 0.5;
+        int i = cv_floor(f);
+        ofs[v] = 0; c1[v] = 0;
+        if (i >= 0 && ssize > 1) {
+            if (i < ssize - 1) { ofs[v] = i; c1[v] = cv_round((f - i) * 256); }
+            else ofs[v] = ssize - 1;
+        }
+    }
+}
+
+void orc_resize_linear_exact_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride)
+{
+    int32_t* xo = malloc(sizeof(int32_t) * dw); int32_t* xa = malloc(sizeof(int32_t) * dw);
+    int32_t* yo = malloc(sizeof(int32_t) * dh); int32_t* ya = malloc(sizeof(int32_t) * dh);
+    exact_coeffs(sw, dw, xo, xa); exact_coeffs(sh, dh, yo, ya);
+    for (int dy = 0; dy < dh; ++dy) {
+        int y0 = yo[dy], y1 = y0 + 1 < sh ? y0 + 1 : sh - 1, b1 = ya[dy], b0 = 256 - b1;
+        const uint8_t* S0 = src + (size_t)y0 * sstride; const uint8_t* S1 = src + (size_t)y1 * sstride;
+        for (int dx = 0; dx < dw; ++dx) {
+            int x0 = xo[dx], x1 = x0 + 1 < sw ? x0 + 1 : sw - 1, a1 = xa[dx], a0 = 256 - a1;
+            int h0 = S0[x0] * a0 + S0[x1] * a1, h1 = S1[x0] * a0 + S1[x1] * a1;
+            dst[(size_t)dy * dstride + dx] = (uint8_t)((h0 * b0 + h1 * b1 + (1 << 15)) >> 16);
+        }
+    }
+    free(xo); free(xa); free(yo); free(ya);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -448,6 +495,7 @@ typedef struct {
     int32_t nfeatures, nlevels, fast_threshold, edge_threshold;
     float scale_factor;
     int32_t blur_mode;   /* 0: OpenCV-2.4 8-bit fixed point (reference parity); 1: float path (cv >= 3.4) */
+    int32_t pyramid_mode;/* 0: OpenCV-2.4 INTER_LINEAR (reference parity); 1: INTER_LINEAR_EXACT + cv4 level sizes (cv >= 3.4) */
 } orc_orb_params;
 
 int orc_orb_extract(const uint8_t* img, int W, int H, int stride, const orc_orb_params* prm,
@@ -457,7 +505,8 @@ int orc_orb_extract(const uint8_t* img, int W, int H, int stride, const orc_orb_
 {
     int L = prm->nlevels;
     int32_t lw[32], lh[32], quota[32];
-    orc_level_sizes(W, H, L, prm->scale_factor, lw, lh);
+    if (prm->pyramid_mode == 1) orc_level_sizes_cv4(W, H, L, prm->scale_factor, lw, lh);
+    else orc_level_sizes(W, H, L, prm->scale_factor, lw, lh);
     orc_level_quotas(prm->nfeatures, L, prm->scale_factor, quota);
     uint8_t* prev = NULL; int n = 0;
     size_t out_off = 0;
@@ -465,6 +514,7 @@ int orc_orb_extract(const uint8_t* img, int W, int H, int stride, const orc_orb_
         int w = lw[l], h = lh[l];
         uint8_t* cur = malloc((size_t)w * h);
         if (l == 0) for (int y = 0; y < h; ++y) memcpy(cur + (size_t)y * w, img + (size_t)y * stride, w);
+        else if (prm->pyramid_mode == 1) orc_resize_linear_exact_u8(prev, lw[l - 1], lh[l - 1], lw[l - 1], cur, w, h, w);
         else orc_resize_linear_u8(prev, lw[l - 1], lh[l - 1], lw[l - 1], cur, w, h, w);
         if (pyr_out) memcpy(pyr_out + out_off, cur, (size_t)w * h);
         int level_n = 0;

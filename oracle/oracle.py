@@ -52,12 +52,12 @@ def _p(a):
 
 class OrbParams(C.Structure):
     _fields_ = [("nfeatures", C.c_int32), ("nlevels", C.c_int32), ("fast_threshold", C.c_int32),
-                ("edge_threshold", C.c_int32), ("scale_factor", C.c_float), ("blur_mode", C.c_int32)]
+                ("edge_threshold", C.c_int32), ("scale_factor", C.c_float), ("blur_mode", C.c_int32), ("pyramid_mode", C.c_int32)]
 
 
-def level_sizes(W, H, nlevels, scale=1.2):
+def level_sizes(W, H, nlevels, scale=1.2, cv4=False):
     lw = np.zeros(nlevels, np.int32); lh = np.zeros(nlevels, np.int32)
-    lib().orc_level_sizes(W, H, nlevels, C.c_float(scale), _p(lw), _p(lh))
+    (lib().orc_level_sizes_cv4 if cv4 else lib().orc_level_sizes)(W, H, nlevels, C.c_float(scale), _p(lw), _p(lh))
     return lw, lh
 
 
@@ -75,6 +75,13 @@ def resize_linear(src, dw, dh):
     src = np.ascontiguousarray(src, np.uint8)
     dst = np.zeros((dh, dw), np.uint8)
     lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def resize_linear_exact(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_exact_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
     return dst
 
 
@@ -139,12 +146,12 @@ def brief_pattern():
 
 
 def orb_extract(img, nfeatures=1000, nlevels=8, fast_threshold=20, edge_threshold=31, scale=1.2,
-                want_levels=False, blur_mode=0):
+                want_levels=False, blur_mode=0, pyramid_mode=0):
     """Whole-image ORB in canonical order.  Returns (keypoints[KEYPOINT_DTYPE], desc[n,32], extras)."""
     img = np.ascontiguousarray(img, np.uint8)
     H, W = img.shape
-    prm = OrbParams(nfeatures, nlevels, fast_threshold, edge_threshold, scale, blur_mode)
-    lw, lh = level_sizes(W, H, nlevels, scale)
+    prm = OrbParams(nfeatures, nlevels, fast_threshold, edge_threshold, scale, blur_mode, pyramid_mode)
+    lw, lh = level_sizes(W, H, nlevels, scale, cv4=(pyramid_mode == 1))
     P = int((lw.astype(np.int64) * lh).sum())
     cap = int(4 * nfeatures + 4096)
     while True:

@@ -63,6 +63,17 @@ def main():
         d["kp_%d" % i] = kp_array(kp); d["desc_%d" % i] = desc if desc is not None else np.zeros((0, 32), np.uint8)
     np.savez_compressed(os.path.join(OUT, "orb_nl1.npz"), n=4, **d)
 
+    # 4b. cv2.ORB end to end with the full pyramid (cv4 arithmetic: INTER_LINEAR_EXACT pyramid + float blur):
+    #     pins the multi-level logic (level sizes, quotas, per-level selection, coordinate scaling)
+    d = {}
+    full = synth.CorridorScene(seed=0, width=1241, height=376).frame(1)[0]
+    for i, (img, nf, nl, th) in enumerate(((full, 1000, 8, 20), (l0, 300, 4, 20), (r0, 250, 3, 12))):
+        orb = cv2.ORB_create(nfeatures=nf, nlevels=nl, fastThreshold=th)
+        kp, desc = orb.detectAndCompute(img, None)
+        d["img_%d" % i] = img; d["nf_%d" % i] = nf; d["nl_%d" % i] = nl; d["th_%d" % i] = th
+        d["kp_%d" % i] = kp_array(kp); d["desc_%d" % i] = desc
+    np.savez_compressed(os.path.join(OUT, "orb_multilevel.npz"), n=3, **d)
+
     # 5. BFMatcher(NORM_HAMMING): random descriptors with planted near-duplicates and exact ties
     Q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
     T = rng.integers(0, 256, (257, 32), dtype=np.uint8)

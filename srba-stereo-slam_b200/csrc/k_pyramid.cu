@@ -2,6 +2,8 @@
 //
 // Replaces the pyramid construction inside cv::ORB::operator() reached through
 // m_voEngine.processNewImagePair (reference src/CSRBAStereoSLAMEstimator.cpp:112,267; nlevels from :1141).
+// Two arithmetic modes (sfe_config.pyramid_mode): OpenCV-2.4 INTER_LINEAR (below; what the reference links) and
+// OpenCV>=3.4 INTER_LINEAR_EXACT (8-bit fractions, (b0*h0 + b1*h1 + 2^15) >> 16; what cv2 4.13's ORB runs; pinned).
 // Arithmetic: horizontal pass S[sx]*a0 + S[sx+1]*a1 with 11-bit coefficients into
 // int32, vertical pass (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.  The coefficient tables
 // are computed on the host exactly as OpenCV does (double/float) so the kernel is pure integer.
@@ -23,6 +25,7 @@ struct PyrArgs {
 
 #define PYR_TPW (PYR_BOX_W / 4)      // tile pitch in words
 
+template <int MODE>
 __global__ void __launch_bounds__(256)
 pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
 {
@@ -63,8 +66,10 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
         const uint32_t* row = tile + r * PYR_TPW + wi;
         const uint32_t A = __funnelshift_r(row[0], row[1], sh), B = __funnelshift_r(row[1], row[2], sh);
         const uint32_t b01 = __byte_perm(A, B, sel & 0xffffu), b23 = __byte_perm(A, B, sel >> 16);
-        const uint32_t h0 = __dp2a_lo(c0, b01, 0u) >> 4, h1 = __dp2a_hi(c1, b01, 0u) >> 4;
-        const uint32_t h2 = __dp2a_lo(c2, b23, 0u) >> 4, h3 = __dp2a_hi(c3, b23, 0u) >> 4;
+        // cv 2.4: the vertical pass consumes (h >> 4); cv4-exact: h itself is the 8.8 fixed-point value (<= 65280)
+        const int hs = MODE == SFE_PYRAMID_CV24_LINEAR ? 4 : 0;
+        const uint32_t h0 = __dp2a_lo(c0, b01, 0u) >> hs, h1 = __dp2a_hi(c1, b01, 0u) >> hs;
+        const uint32_t h2 = __dp2a_lo(c2, b23, 0u) >> hs, h3 = __dp2a_hi(c3, b23, 0u) >> hs;
         *reinterpret_cast<uint2*>(hbuf + r * (PYR_TW / 2) + 2 * gq) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     }
     __syncthreads();
@@ -79,10 +84,19 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
         const uint32_t b0 = (uint32_t)(yt[k].y & 0xffff) << 16, b1 = (uint32_t)(yt[k].y >> 16) << 16;   // (b << 16) * r >> 32 == (b * r) >> 16
         const uint2 u = *reinterpret_cast<const uint2*>(hbuf + r0 * (PYR_TW / 2) + 2 * gq);
         const uint2 v = *reinterpret_cast<const uint2*>(hbuf + r1 * (PYR_TW / 2) + 2 * gq);
-        uint32_t o0 = (__umulhi(b0, u.x & 0xffffu) + __umulhi(b1, v.x & 0xffffu) + 2u) >> 2;
-        uint32_t o1 = (__umulhi(b0, u.x >> 16) + __umulhi(b1, v.x >> 16) + 2u) >> 2;
-        uint32_t o2 = (__umulhi(b0, u.y & 0xffffu) + __umulhi(b1, v.y & 0xffffu) + 2u) >> 2;
-        uint32_t o3 = (__umulhi(b0, u.y >> 16) + __umulhi(b1, v.y >> 16) + 2u) >> 2;
+        uint32_t o0, o1, o2, o3;
+        if (MODE == SFE_PYRAMID_CV24_LINEAR) {
+            o0 = (__umulhi(b0, u.x & 0xffffu) + __umulhi(b1, v.x & 0xffffu) + 2u) >> 2;
+            o1 = (__umulhi(b0, u.x >> 16) + __umulhi(b1, v.x >> 16) + 2u) >> 2;
+            o2 = (__umulhi(b0, u.y & 0xffffu) + __umulhi(b1, v.y & 0xffffu) + 2u) >> 2;
+            o3 = (__umulhi(b0, u.y >> 16) + __umulhi(b1, v.y >> 16) + 2u) >> 2;
+        } else {                                       // (b0*h0 + b1*h1 + 2^15) >> 16, b0 + b1 = 256
+            const uint32_t c0y = b0 >> 16, c1y = b1 >> 16;
+            o0 = (c0y * (u.x & 0xffffu) + c1y * (v.x & 0xffffu) + 32768u) >> 16;
+            o1 = (c0y * (u.x >> 16) + c1y * (v.x >> 16) + 32768u) >> 16;
+            o2 = (c0y * (u.y & 0xffffu) + c1y * (v.y & 0xffffu) + 32768u) >> 16;
+            o3 = (c0y * (u.y >> 16) + c1y * (v.y >> 16) + 32768u) >> 16;
+        }
         const int x = x0 + 4 * gq;
         if (x >= a.dw) o0 = 0; if (x + 1 >= a.dw) o1 = 0; if (x + 2 >= a.dw) o2 = 0; if (x + 3 >= a.dw) o3 = 0;   // deterministic padding
         uint8_t* D = a.dst + (size_t)img * a.dimg_bytes + (size_t)dy * a.dpitch + x;
@@ -98,7 +112,8 @@ void launch_pyramid_level(sfe_context* c, int level, int nimg)
     a.dw = g.w; a.dh = g.h; a.sh = c->pack.g[level - 1].h;
     a.gtab = c->d_gtab[level]; a.ytab = c->d_ytab[level];
     dim3 grid((g.w + PYR_TW - 1) / PYR_TW, (g.h + PYR_TH - 1) / PYR_TH, nimg);
-    pyramid_kernel<<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
+    if (c->cfg.pyramid_mode == SFE_PYRAMID_CV4_EXACT) pyramid_kernel<SFE_PYRAMID_CV4_EXACT><<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
+    else pyramid_kernel<SFE_PYRAMID_CV24_LINEAR><<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
     c->launches++;
 }
 

@@ -28,7 +28,7 @@ extern "C" void sfe_default_config(sfe_config* c)
     c->scale_factor = 1.2f; c->edge_threshold = 31; c->fast_threshold = 20;
     c->blur_mode = SFE_BLUR_CV24_FIXED; c->max_pairs = 1;
     c->max_y_diff = 2.0f; c->min_disparity = 0.0f; c->max_disparity = 1e9f;
-    c->orb_max_distance = 60; c->robust_1to1 = 0; c->device = 0; c->use_graph = 1;
+    c->orb_max_distance = 60; c->robust_1to1 = 0; c->device = 0; c->use_graph = 1; c->pyramid_mode = SFE_PYRAMID_CV24_LINEAR;
 }
 
 extern "C" const char* sfe_last_error(const sfe_context* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -52,6 +52,24 @@ static void build_resize_table(int ssize, int dsize, bool is_x, std::vector<int2
         const int a0 = cv_round_d(c0 * 2048), a1 = cv_round_d(c1 * 2048);
         tab[d].x = s;
         tab[d].y = (a0 & 0xffff) | (a1 << 16);
+    }
+}
+
+// INTER_LINEAR_EXACT (OpenCV >= 3.4): 8-bit fractions, edge samples taken with full weight.
+static void build_resize_table_exact(int ssize, int dsize, std::vector<int2>& tab)
+{
+    tab.resize(dsize);
+    const double inv = (double)dsize / ssize, scale = 1.0 / inv;
+    for (int v = 0; v < dsize; ++v) {
+        const double f = scale * ((double)v + 0.5) - 0.5;
+        const int i = cv_floor_d(f);
+        int ofs = 0, c1 = 0;
+        if (i >= 0 && ssize > 1) {
+            if (i < ssize - 1) { ofs = i; c1 = cv_round_d((f - i) * 256); }
+            else ofs = ssize - 1;
+        }
+        tab[v].x = ofs;
+        tab[v].y = ((256 - c1) & 0xffff) | (c1 << 16);
     }
 }
 
@@ -86,6 +104,7 @@ static int create_impl(sfe_context* c)
     if (f.max_pairs < 1 || f.max_pairs > 16384) { c->err = "max_pairs must be in [1,16384]"; return SFE_ERR_INVALID; }
     if (f.fast_threshold < 1 || f.fast_threshold > 127) { c->err = "fast_threshold must be in [1,127]"; return SFE_ERR_INVALID; }
     if (f.blur_mode != SFE_BLUR_CV24_FIXED && f.blur_mode != SFE_BLUR_FLOAT) { c->err = "bad blur_mode"; return SFE_ERR_INVALID; }
+    if (f.pyramid_mode != SFE_PYRAMID_CV24_LINEAR && f.pyramid_mode != SFE_PYRAMID_CV4_EXACT) { c->err = "bad pyramid_mode"; return SFE_ERR_INVALID; }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= f.device) { c->err = "no usable CUDA device (there is no CPU fallback)"; return SFE_ERR_CUDA; }
@@ -117,9 +136,14 @@ static int create_impl(sfe_context* c)
     for (int l = 0; l < L; ++l) {
         LevelGeom& g = P.g[l];
         g.scale = (float)pow((double)f.scale_factor, (double)l);
-        const float inv = 1 / g.scale;
-        g.w = cv_round_d((double)((float)f.width * inv));
-        g.h = cv_round_d((double)((float)f.height * inv));
+        if (f.pyramid_mode == SFE_PYRAMID_CV4_EXACT) {          // cv >= 3: Size(cvRound(cols/scale), cvRound(rows/scale))
+            g.w = cv_round_d((double)((float)f.width / g.scale));
+            g.h = cv_round_d((double)((float)f.height / g.scale));
+        } else {                                                // cv 2.4: scale = 1/getScale(level); cvRound(cols*scale)
+            const float inv = 1 / g.scale;
+            g.w = cv_round_d((double)((float)f.width * inv));
+            g.h = cv_round_d((double)((float)f.height * inv));
+        }
         g.pitch = (g.w + 127) / 128 * 128;
         g.img_bytes = (size_t)g.pitch * g.h;
         g.lvl_ofs = arena;
@@ -182,8 +206,13 @@ static int create_impl(sfe_context* c)
     // ---- resize tables ------------------------------------------------------------------------
     c->xtab.resize(L); c->ytab.resize(L);
     for (int l = 1; l < L; ++l) {
-        build_resize_table(P.g[l - 1].w, P.g[l].w, true, c->xtab[l]);
-        build_resize_table(P.g[l - 1].h, P.g[l].h, false, c->ytab[l]);
+        if (f.pyramid_mode == SFE_PYRAMID_CV4_EXACT) {
+            build_resize_table_exact(P.g[l - 1].w, P.g[l].w, c->xtab[l]);
+            build_resize_table_exact(P.g[l - 1].h, P.g[l].h, c->ytab[l]);
+        } else {
+            build_resize_table(P.g[l - 1].w, P.g[l].w, true, c->xtab[l]);
+            build_resize_table(P.g[l - 1].h, P.g[l].h, false, c->ytab[l]);
+        }
         // footprint check against the fixed TMA box
         for (int x0 = 0; x0 < P.g[l].w; x0 += PYR_TW) {
             const int x1 = std::min(x0 + PYR_TW, P.g[l].w) - 1;

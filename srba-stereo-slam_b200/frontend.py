@@ -22,6 +22,7 @@ COUNTS_DTYPE = np.dtype([("n_left", "<i4"), ("n_right", "<i4"), ("n_matches", "<
 
 SFE_OK, SFE_ERR_INVALID, SFE_ERR_CUDA, SFE_ERR_CAPACITY, SFE_ERR_STATE = range(5)
 BLUR_CV24_FIXED, BLUR_FLOAT = 0, 1
+PYRAMID_CV24_LINEAR, PYRAMID_CV4_EXACT = 0, 1
 
 
 class SfeConfig(C.Structure):
@@ -29,7 +30,7 @@ class SfeConfig(C.Structure):
                 ("scale_factor", C.c_float), ("edge_threshold", C.c_int32), ("fast_threshold", C.c_int32),
                 ("blur_mode", C.c_int32), ("max_pairs", C.c_int32), ("max_y_diff", C.c_float),
                 ("min_disparity", C.c_float), ("max_disparity", C.c_float), ("orb_max_distance", C.c_int32),
-                ("robust_1to1", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32)]
+                ("robust_1to1", C.c_int32), ("device", C.c_int32), ("use_graph", C.c_int32), ("pyramid_mode", C.c_int32)]
 
 
 class SfeError(RuntimeError):

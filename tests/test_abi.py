@@ -28,7 +28,7 @@ def test_pod_layouts_match_opencv():
     assert frontend.KEYPOINT_DTYPE.itemsize == 28 and frontend.DMATCH_DTYPE.itemsize == 16     # cv::KeyPoint / cv::DMatch
     assert list(frontend.KEYPOINT_DTYPE.names) == ["x", "y", "size", "angle", "response", "octave", "class_id"]
     assert list(frontend.DMATCH_DTYPE.names) == ["queryIdx", "trainIdx", "imgIdx", "distance"]
-    assert ctypes.sizeof(frontend.SfeConfig) == 16 * 4
+    assert ctypes.sizeof(frontend.SfeConfig) == 17 * 4
 
 
 def test_default_config_is_kitti_ini():

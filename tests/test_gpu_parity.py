@@ -104,6 +104,31 @@ def test_golden_cv2_orb_single_level(mods, golden):
         assert np.array_equal(m["queryIdx"], m["trainIdx"]) and np.all(m["distance"] == 0) and len(m) == len(kl)
 
 
+def test_golden_cv2_orb_multilevel(mods, golden):
+    """The CUDA path in cv4 arithmetic (pyramid_mode 1 + blur_mode 1) against the committed cv2.ORB outputs at
+    8 / 4 / 3 levels: every keypoint field and descriptor bit identical, end to end."""
+    frontend, orc = mods
+    g = golden("orb_multilevel.npz")
+    for i in range(int(g["n"])):
+        img = g["img_%d" % i]
+        h, w = img.shape
+        fe = frontend.StereoFrontEnd(width=w, height=h, nlevels=int(g["nl_%d" % i]), nfeatures=int(g["nf_%d" % i]),
+                                     fast_threshold=int(g["th_%d" % i]), blur_mode=1, pyramid_mode=1, max_pairs=1)
+        try:
+            fe.process_stereo(img, img)
+            kl, kr, dl, dr, m = fe.get_values(0)
+        finally:
+            fe.close()
+        ref, rdesc = g["kp_%d" % i], g["desc_%d" % i]
+        sc = np.array([orc.level_scale(int(o)) for o in ref[:, 5]])
+        o = np.lexsort((np.rint(ref[:, 0] / sc), np.rint(ref[:, 1] / sc), ref[:, 5]))
+        ref, rdesc = ref[o], rdesc[o]
+        assert len(kl) == len(ref) > 100
+        for j, f in enumerate(("x", "y", "size", "angle", "response", "octave", "class_id")):
+            assert np.array_equal(kl[f], ref[:, j].astype(kl[f].dtype)), (i, f)
+        assert np.array_equal(dl, rdesc) and np.array_equal(dr, rdesc)
+
+
 def test_runtime_thresholds_and_repeat(mods, scene_frames):
     """setFASTThreshold / setORBThreshold + request.repeat (EST.cpp:263-315)."""
     frontend, orc = mods

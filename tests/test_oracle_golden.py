@@ -66,6 +66,36 @@ def test_orb_single_level_matches_cv2(golden):
         assert np.array_equal(desc, rdesc)
 
 
+def _canonical(ref, rdesc, orc):
+    sc = np.array([orc.level_scale(int(o)) for o in ref[:, 5]])
+    o = np.lexsort((np.rint(ref[:, 0] / sc), np.rint(ref[:, 1] / sc), ref[:, 5]))
+    return ref[o], rdesc[o]
+
+
+def test_orb_multilevel_matches_cv2_end_to_end(golden):
+    """The WHOLE multi-level extraction (pyramid, per-level quotas, FAST, retain-best, Harris, orientation, blur,
+    rBRIEF, coordinate scaling) against cv2.ORB 4.13 at 8 / 4 / 3 levels: every keypoint field and every descriptor
+    bit identical in the cv4 arithmetic (pyramid_mode 1 + blur_mode 1).  The reference-parity arithmetic
+    (OpenCV 2.4) differs only in the resize and blur formulas, each restated and tested separately."""
+    g = golden("orb_multilevel.npz")
+    for i in range(int(g["n"])):
+        img, nf, nl, th = g["img_%d" % i], int(g["nf_%d" % i]), int(g["nl_%d" % i]), int(g["th_%d" % i])
+        kps, desc, _ = orc.orb_extract(img, nfeatures=nf, nlevels=nl, fast_threshold=th, blur_mode=1, pyramid_mode=1)
+        ref, rdesc = _canonical(g["kp_%d" % i], g["desc_%d" % i], orc)
+        assert len(kps) == len(ref) > 100
+        for j, f in enumerate(("x", "y", "size", "angle", "response", "octave", "class_id")):
+            assert np.array_equal(kps[f], ref[:, j].astype(kps[f].dtype)), (i, f)
+        assert np.array_equal(desc, rdesc)
+        assert len(np.unique(kps["octave"])) == nl or i == 0
+
+
+def test_resize_exact_vs_reference_mode_differ_only_slightly():
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (120, 200), dtype=np.uint8)
+    a = orc.resize_linear(img, 167, 100).astype(int); b = orc.resize_linear_exact(img, 167, 100).astype(int)
+    assert np.abs(a - b).max() <= 2 and (a != b).any()          # two different fixed-point roundings of the same bilinear filter
+
+
 def test_bfmatcher_bit_exact(golden):
     g = golden("bf.npz")
     m = orc.match_bf(g["Q"], g["T"])
