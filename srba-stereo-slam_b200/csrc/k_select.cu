@@ -26,6 +26,32 @@ __device__ __forceinline__ float float_from_key(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Warp-parallel "k-th from the top" over a 256-bin shared histogram (call with all 32 lanes of one warp):
+// returns the largest bin b with sum_{i >= b} hist[i] >= k, and `above` = sum_{i > b} hist[i].
+// If the total is below k, bin 0 is returned with above = total - hist[0].
+__device__ __forceinline__ void kth_from_top(const int* hist, int k, int lane, int& bin, int& above)
+{
+    const int base = 8 * (31 - lane);                 // lane 0 owns the top 8 bins
+    int h[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[j] = hist[base + j]; s += h[j]; }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    const int excl = incl - s;
+    const uint32_t bal = __ballot_sync(0xffffffffu, incl >= k && excl < k);
+    const int src = bal ? __ffs(bal) - 1 : 31;
+    int b = base, ab = excl + s - h[0];                // default: lowest bin of the group
+    int cum = excl;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+        if (cum + h[j] >= k) { b = base + j; ab = cum; break; }
+        cum += h[j];
+    }
+    bin = __shfl_sync(0xffffffffu, b, src);
+    above = __shfl_sync(0xffffffffu, ab, src);
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr,
               const uint32_t* __restrict__ raw, const int32_t* __restrict__ raw_count,
@@ -53,22 +79,27 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     __syncthreads();
     for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&hist[rl[i] >> 24], 1);
     __syncthreads();
-    if (tid == 0) {
-        int thr = 0;
+    if (warp == 0) {
+        int thr = 0, above = 0;
         if (n > 2 * q) {
-            int cum = 0;
-            for (int s = 255; s >= 0; --s) { cum += hist[s]; if (cum >= 2 * q) { thr = s; break; } }
+            kth_from_top(hist, 2 * q, lane, thr, above);
             if (q == 0) thr = 256;
         }
-        s_thr = thr;
+        if (lane == 0) s_thr = thr;
     }
     __syncthreads();
     const int thr = s_thr;
-    for (int i = tid; i < n; i += SEL_THREADS) {
-        const uint32_t r = rl[i];
-        if ((int)(r >> 24) >= thr) {
-            const int idx = atomicAdd(&s_n, 1);
-            if (idx < cand_cap) cand_xy[idx] = (((r >> 12) & 0xfffu) << 16) | (r & 0xfffu);
+    for (int base = 0; base < n; base += SEL_THREADS) {          // warp-aggregated compaction
+        const int i = base + tid;
+        uint32_t r = 0; bool keepc = false;
+        if (i < n) { r = rl[i]; keepc = (int)(r >> 24) >= thr; }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keepc);
+        if (bal) {
+            int wb = 0;
+            if (lane == 0) wb = atomicAdd(&s_n, __popc(bal));
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            const int idx = wb + __popc(bal & ((1u << lane) - 1u));
+            if (keepc && idx < cand_cap) cand_xy[idx] = (((r >> 12) & 0xfffu) << 16) | (r & 0xfffu);
         }
     }
     __syncthreads();
@@ -130,11 +161,11 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
                 if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
             }
             __syncthreads();
-            if (tid == 0) {
-                int k = s_k, cum = 0, b = 255;
-                for (; b > 0; --b) { if (cum + hist[b] >= k) break; cum += hist[b]; }
-                s_k = k - cum;
-                s_prefix = prefix | ((uint32_t)b << shift);
+            if (warp == 0) {
+                int b, above;
+                kth_from_top(hist, s_k, lane, b, above);
+                __syncwarp();
+                if (lane == 0) { s_k = s_k - above; s_prefix = prefix | ((uint32_t)b << shift); }
             }
             mask |= 255u << shift;
             __syncthreads();
@@ -151,12 +182,17 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     __shared__ float sval[SEL_SORT_CAP];
     if (tid == 0) s_n = 0;
     __syncthreads();
-    int nkept_local = 0;
-    for (int i = tid; i < nc; i += SEL_THREADS) {
-        if (!(cand_resp[i] >= boundary)) continue;
-        const int slot = atomicAdd(&s_n, 1);
-        if (slot < SEL_SORT_CAP) { skey[slot] = cand_xy[i]; sval[slot] = cand_resp[i]; }
-        ++nkept_local;
+    for (int base = 0; base < nc; base += SEL_THREADS) {          // warp-aggregated compaction of the kept points
+        const int i = base + tid;
+        const bool kp = i < nc && cand_resp[i] >= boundary;
+        const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+        if (bal) {
+            int wb = 0;
+            if (lane == 0) wb = atomicAdd(&s_n, __popc(bal));
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            const int slot = wb + __popc(bal & ((1u << lane) - 1u));
+            if (kp && slot < SEL_SORT_CAP) { skey[slot] = cand_xy[i]; sval[slot] = cand_resp[i]; }
+        }
     }
     __syncthreads();
     const int nk_all = s_n;
