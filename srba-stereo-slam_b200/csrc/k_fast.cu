@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t nibble_of_flags(uint32_t f80)               
 #define FAST_TP (FAST_BOX_W / 4)         // tile pitch in words
 #define FAST_AK ((FAST_SH * FAST_WJ + 255) / 256)   // score words per thread in phase A (<= 8: 4 flag bits each)
 
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(256, 6)
 fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint32_t* __restrict__ raw,
             int32_t* __restrict__ raw_count, const int th)
 {
