@@ -322,6 +322,18 @@ def main():
     for f in extra:
         f.close()
 
+    # ---- the reference's own call shape: one stereo pair per call (processNewImagePair + getValues), host buffers ----------
+    fe1 = frontend.StereoFrontEnd(width=W, height=H, nlevels=NLEVELS, nfeatures=NFEAT, max_pairs=1, device=local)
+    lat = []
+    for i in range(25):
+        t0 = time.perf_counter()
+        fe1.process_stereo(frames[i % B, 0], frames[i % B, 1])
+        fe1.get_values(0)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    fe1.close()
+    single = {"ms_per_pair_median": float(np.median(lat[5:])), "frames_per_s": 1e3 / float(np.median(lat[5:])),
+              "note": "sfe_process_stereo + sfe_get_values on pageable host images, synchronous, batch of 1 (the live SLAM loop's shape)"}
+
     # ---- per-kernel times, live (CUDA events around each stage, direct launches) --------------------------------
     fe.set_profiling(True)
     acc = {}
@@ -383,7 +395,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps, "matches_read_back": nmatch,
                         "h2d_link_GBps_measured": h2d_gbs,
                         "timing": "host wall clock between full synchronisations; 3 contexts pipeline PCIe against kernels"},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "full_frontend": full}
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "full_frontend": full, "single_pair_latency": single}
         print(json.dumps(line))
     fe.close()
     if dist is not None:

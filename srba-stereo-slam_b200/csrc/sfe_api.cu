@@ -488,8 +488,18 @@ extern "C" int sfe_process_stereo(sfe_context* c, const uint8_t* left, const uin
         const LevelGeom& g = c->pack.g[0];
         if (stride < (size_t)g.w) { c->err = "bad stride"; return SFE_ERR_INVALID; }
         stage_mark(c, ST_H2D);
-        SFE_CUDA(c, cudaMemcpy2DAsync(c->d_pyr + g.lvl_ofs, g.pitch, left, stride, g.w, g.h, cudaMemcpyHostToDevice, c->stream));
-        SFE_CUDA(c, cudaMemcpy2DAsync(c->d_pyr + g.lvl_ofs + g.img_bytes, g.pitch, right, stride, g.w, g.h, cudaMemcpyHostToDevice, c->stream));
+        if (stride == (size_t)g.w) {
+            // tightly packed rows: two linear DMAs into the packed staging + the unpack kernel (a pitched copy costs one
+            // DMA descriptor per row)
+            const size_t bytes = (size_t)g.w * g.h;
+            if (!c->d_packed) SFE_CUDA(c, dalloc(&c->d_packed, (size_t)c->NI * bytes));
+            SFE_CUDA(c, cudaMemcpyAsync(c->d_packed, left, bytes, cudaMemcpyHostToDevice, c->stream));
+            SFE_CUDA(c, cudaMemcpyAsync(c->d_packed + bytes, right, bytes, cudaMemcpyHostToDevice, c->stream));
+            launch_unpack(c, 2);
+        } else {
+            SFE_CUDA(c, cudaMemcpy2DAsync(c->d_pyr + g.lvl_ofs, g.pitch, left, stride, g.w, g.h, cudaMemcpyHostToDevice, c->stream));
+            SFE_CUDA(c, cudaMemcpy2DAsync(c->d_pyr + g.lvl_ofs + g.img_bytes, g.pitch, right, stride, g.w, g.h, cudaMemcpyHostToDevice, c->stream));
+        }
     } else if (!c->have_results) { c->err = "repeat without a previous frame"; return SFE_ERR_STATE; }
     int r = run_batch(c, 1);
     if (r) return r;
