@@ -95,3 +95,50 @@ def test_project_match_to_3d(host):
         assert xyz.tolist() == list(dao.project_match_to_3d(ul, vl, ur, *cam))
     host.srba_project_match_to_3d(700.0, 200.0, 680.0, _p(cam), _p(xyz))
     assert abs(xyz[2] - 0.54 * 707.0912 / 20.0) < 1e-9                 # Z = B f / disparity
+
+
+def test_keyframe_stream_format_is_byte_compatible(host, tmp_path):
+    """EST.cpp:2517-2616: size_t n; {x, y, response, size, angle, octave, class_id}; int rows, cols, type; bytes ...
+    then matches as {size_t id; int queryIdx, trainIdx; float distance; int imgIdx}.  Written by the C++ code, parsed
+    here byte by byte with the reference's layout, then loaded back by the C++ code."""
+    import struct
+    from srba_stereo_slam_b200 import frontend
+    rng = np.random.default_rng(5)
+    nl, nr, nm = 7, 5, 4
+
+    def kps(n):
+        k = np.zeros(n, frontend.KEYPOINT_DTYPE)
+        for f in ("x", "y", "size", "angle", "response"):
+            k[f] = rng.uniform(0, 400, n).astype(np.float32)
+        k["octave"] = rng.integers(0, 8, n); k["class_id"] = -1
+        return k
+    kl, kr = kps(nl), kps(nr)
+    dl = rng.integers(0, 256, (nl, 32), dtype=np.uint8); dr = rng.integers(0, 256, (nr, 32), dtype=np.uint8)
+    m = np.zeros(nm, frontend.DMATCH_DTYPE); m["queryIdx"] = [0, 2, 3, 6]; m["trainIdx"] = [1, 0, 4, 2]; m["distance"] = [3, 17, 40, 59]
+    ids = np.array([100, 7, 2**40 + 5, 3], np.uint64)
+    path = str(tmp_path / "kf.bin").encode()
+    assert host.srba_kf_dump_file(path, _p(kl), nl, _p(kr), nr, _p(dl), _p(dr), _p(m), nm, _p(ids)) == 0
+    raw = open(path, "rb").read(); off = 0
+    for k, d in ((kl, dl), (kr, dr)):
+        (n,) = struct.unpack_from("<Q", raw, off); off += 8
+        assert n == len(k)
+        for i in range(n):
+            x, y, resp, size, ang, octv, cid = struct.unpack_from("<5f2i", raw, off); off += 28
+            assert (x, y, resp, size, ang, octv, cid) == (k["x"][i], k["y"][i], k["response"][i], k["size"][i], k["angle"][i], k["octave"][i], k["class_id"][i])
+        rows, cols, typ = struct.unpack_from("<3i", raw, off); off += 12
+        assert (rows, cols, typ) == (len(k), 32, 0)                         # CV_8U == 0
+        assert raw[off:off + rows * cols] == d.tobytes(); off += rows * cols
+    (n,) = struct.unpack_from("<Q", raw, off); off += 8
+    assert n == nm
+    for i in range(nm):
+        mid, q, t, dist, img = struct.unpack_from("<Q2ifi", raw, off); off += 24
+        assert (mid, q, t, dist, img) == (int(ids[i]), m["queryIdx"][i], m["trainIdx"][i], m["distance"][i], m["imgIdx"][i])
+    assert off == len(raw)
+    kl2, kr2 = np.zeros(16, frontend.KEYPOINT_DTYPE), np.zeros(16, frontend.KEYPOINT_DTYPE)
+    dl2, dr2 = np.zeros((16, 32), np.uint8), np.zeros((16, 32), np.uint8)
+    m2 = np.zeros(16, frontend.DMATCH_DTYPE); ids2 = np.zeros(16, np.uint64)
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    assert host.srba_kf_load_file(path, _p(kl2), C.byref(a), _p(kr2), C.byref(b), _p(dl2), _p(dr2), _p(m2), C.byref(c), _p(ids2), 16) == 0
+    assert (a.value, b.value, c.value) == (nl, nr, nm)
+    assert np.array_equal(kl2[:nl], kl) and np.array_equal(kr2[:nr], kr) and np.array_equal(dl2[:nl], dl) and np.array_equal(dr2[:nr], dr)
+    assert np.array_equal(m2[:nm], m) and np.array_equal(ids2[:nm], ids)
