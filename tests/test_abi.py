@@ -63,3 +63,20 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "frontend_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
                 assert "../oracle" not in text and "oracle/" not in text, f
+
+
+def test_library_is_sm100a_native_with_tma():
+    """The shipped cubin is sm_100a only (no fallback architectures) and stages its tiles with TMA
+    (UTMALDG = cp.async.bulk.tensor, SYNCS = mbarrier), uses DP4A/DP2A and packed 16-bit min/max."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "srba-stereo-slam_b200", "libsrba_b200.so")
+    archs = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in archs and not re.search(r"sm_(?!100a)\d+", archs), archs
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert sass.count("UTMALDG") >= 4                       # pyramid (2 modes), FAST, blur (2 modes)
+    assert "SYNCS.ARRIVE.TRANS64" in sass and "IDP.4A" in sass and "IDP.2A" in sass
+    assert "VIMNMX" in sass and "VABSDIFF4" in sass and "POPC" in sass
+    assert "HMMA" not in sass and "UTCHMMA" not in sass     # integer / popc work: tensor cores deliberately unused

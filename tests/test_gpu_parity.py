@@ -291,3 +291,32 @@ def test_full_batch_properties(mods, scene_frames):
         assert np.all(self_m["distance"] == 0) and np.all(self_m["trainIdx"] <= self_m["queryIdx"])
     finally:
         fe.close()
+
+
+def test_abi_error_paths(mods, scene_frames):
+    """Integer status codes across the ABI (no exceptions): call-order and argument errors are reported, not UB."""
+    frontend, _ = mods
+    fe = frontend.StereoFrontEnd(width=320, height=240, nlevels=2, nfeatures=100, max_pairs=2)
+    try:
+        with pytest.raises(frontend.SfeError) as e:
+            fe.get_values(0)                                            # nothing processed yet
+        assert e.value.code == frontend.SFE_ERR_STATE
+        with pytest.raises(frontend.SfeError) as e:
+            fe.process_stereo(None, None, repeat=True)                  # repeat without a previous frame
+        assert e.value.code == frontend.SFE_ERR_STATE
+        with pytest.raises(frontend.SfeError) as e:
+            fe.process_device(3)                                        # more pairs than the context was sized for
+        assert e.value.code == frontend.SFE_ERR_INVALID
+        with pytest.raises(frontend.SfeError):
+            fe.set_fast_threshold(0)
+        rng = np.random.default_rng(0)
+        img = (rng.random((2, 240, 320)) * 255).astype(np.uint8)
+        fe.process_stereo(img[0], img[1])
+        with pytest.raises(frontend.SfeError) as e:
+            fe.get_values(1)                                            # only pair 0 exists
+        assert e.value.code == frontend.SFE_ERR_INVALID
+        kl = fe.get_values(0)[0]
+        assert len(kl) > 0                                              # the context is still usable after the errors
+        assert len(fe.match_bf(np.zeros((0, 32), np.uint8), np.zeros((5, 32), np.uint8))) == 0
+    finally:
+        fe.close()
