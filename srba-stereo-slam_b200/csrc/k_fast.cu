@@ -123,16 +123,17 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
             RINGP(8, -3 * FAST_BOX_W);      RINGP(9, -3 * FAST_BOX_W - 1);  RINGP(10, -2 * FAST_BOX_W - 2); RINGP(11, -FAST_BOX_W - 3);
             RINGP(12, -3);                  RINGP(13, FAST_BOX_W - 3);      RINGP(14, 2 * FAST_BOX_W - 2);  RINGP(15, 3 * FAST_BOX_W - 1);
 #undef RINGP
-            uint32_t m2[16], m4[16], best = 0x80008000u;               // (-32768, -32768)
+            // window-9 min as 3 x 3 with three-input packed min (VIMNMX3.S16x2): 16 + 16 ops, then a max3 tree
+            uint32_t m3[16], best;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m2[k] = __vmins2(P[k], P[(k + 1) & 15]);
+            for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(P[k], P[(k + 1) & 15], P[(k + 2) & 15]);
+            uint32_t m9[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+            for (int k = 0; k < 16; ++k) m9[k] = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            uint32_t t5[5];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t m8 = __vmins2(m4[k], m4[(k + 4) & 15]);
-                best = __vmaxs2(best, __vmins2(m8, P[(k + 8) & 15]));
-            }
+            for (int k = 0; k < 5; ++k) t5[k] = __vimax3_s16x2(m9[3 * k], m9[3 * k + 1], m9[3 * k + 2]);
+            best = __vimax3_s16x2(__vimax3_s16x2(t5[0], t5[1], t5[2]), __vimax3_s16x2(t5[3], t5[4], m9[15]), 0x80008000u);
             const int strength = max((int)(short)(best & 0xffffu), (int)(short)(best >> 16));
             corner = strength > th;
             if (corner) score[pos] = (uint8_t)(strength - 1);
