@@ -320,3 +320,31 @@ def test_abi_error_paths(mods, scene_frames):
         assert len(fe.match_bf(np.zeros((0, 32), np.uint8), np.zeros((5, 32), np.uint8))) == 0
     finally:
         fe.close()
+
+
+def test_strided_and_ragged_batches(mods, scene_frames):
+    """Host images with row/image strides (the generic pitched upload path) and a batch smaller than max_pairs give
+    the same results as the tightly packed full path."""
+    import ctypes as C
+    frontend, _ = mods
+    frames = scene_frames(2, width=640, height=192, seed=3)
+    W, H = 640, 192
+    fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=4, nfeatures=300, max_pairs=8)
+    try:
+        fe.process_batch_host(frames)                                   # packed, 2 of 8 pairs
+        ref = [fe.get_values(p) for p in range(2)]
+        stride, istride = 704, 704 * (H + 5)                            # padded rows and padded images
+        buf = np.full(4 * istride, 255, np.uint8)
+        for i in range(4):
+            view = buf[i * istride:i * istride + H * stride].reshape(H, stride)
+            view[:, :W] = frames.reshape(4, H, W)[i]
+        r = fe.lib.sfe_process_batch_host(fe.h, buf.ctypes.data_as(C.c_void_p), 2, stride, istride)
+        assert r == frontend.SFE_OK
+        for p in range(2):
+            for a, b in zip(ref[p], fe.get_values(p)):
+                assert np.array_equal(a, b)
+        fe.process_stereo(frames[1, 0], frames[1, 1])                   # single-pair entry on the same context
+        for a, b in zip(ref[1], fe.get_values(0)):
+            assert np.array_equal(a, b)
+    finally:
+        fe.close()
