@@ -1,7 +1,9 @@
 #include "da_filters.h"
 #include "CBoWManager.h"
 #include <cmath>
+#include <algorithm>
 #include <deque>
+#include <stdexcept>
 
 // ---- cores on plain arrays (shared by the class-level functions and the C test shims) ----------------------
 static void direction_core(const float* txy, const float* oxy, int n, float offset, int* status)
@@ -136,6 +138,35 @@ void assembleObservations(const CStereoSLAMKF& kf, const TStereoCameraParams& ca
         o.lx = l.pt.x; o.ly = l.pt.y; o.rx = r.pt.x; o.ry = r.pt.y;
         projectMatchTo3D(l.pt.x, l.pt.y, r.pt.x, cam, o.X, o.Y, o.Z);
     }
+}
+
+int processWithAdaptiveThresholds(rso::CStereoOdometryEstimator& vo, rso::CStereoOdometryEstimator::TStereoOdometryRequest& req,
+                                  rso::CStereoOdometryEstimator::TStereoOdometryResult& res, const TAdaptiveThOptions& opt)
+{
+    const size_t octave = 0;
+    int calls = 0;
+    req.repeat = false;
+    do {
+        vo.processNewImagePair(req, res); ++calls;
+        if (res.stereo_matches.empty()) throw std::runtime_error("processNewImagePair failed: " + vo.lastError());
+        if (opt.orb_adaptive_fast_th) {
+            if (int(res.stereo_matches[octave]) < opt.adaptive_th_min_matches) {
+                if (!vo.isFASTThMin()) { vo.setFASTThreshold(std::max(0, vo.getFASTThreshold() - 10)); req.repeat = true; }
+                else if (!vo.isORBThMax()) { vo.setORBThreshold(vo.getORBThreshold() + 10); req.repeat = true; }
+                else if (res.stereo_matches[octave] >= 8) { req.repeat = false; /* limits reached but usable: go on */ }
+                else throw std::runtime_error("The number of found matches is less than the minimum. Aborting");   // EST.cpp:294
+            } else if (res.stereo_matches[octave] < opt.adaptive_th_min_matches * 1.2) {
+                if (!vo.isFASTThMin()) vo.setFASTThreshold(std::max(0, vo.getFASTThreshold() - 5));
+                else if (!vo.isORBThMax()) vo.setORBThreshold(vo.getORBThreshold() + 5);
+                req.repeat = false;
+            } else {
+                vo.setFASTThreshold(std::min(opt.detect_fast_th, vo.getFASTThreshold() + 5));
+                vo.resetORBThreshold();
+                req.repeat = false;
+            }
+        }
+    } while (req.repeat);
+    return calls;
 }
 
 // ---- C shims for the CPU test-suite (ctypes) -----------------------------------------------------------------------

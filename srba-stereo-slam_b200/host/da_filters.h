@@ -47,6 +47,12 @@ void internalDataAssociation(sfe_context* ctx, const CStereoSLAMKF& this_kf, con
 std::pair<size_t, size_t> assignMatchIds(CStereoSLAMKF& new_kf, const TVectorKfsDaInfo& daInfo, const std::vector<size_t>& sorted,
                                          const t_vector_kf& keyframes, size_t& last_match_id);
 
+// The adaptive FAST / ORB threshold loop around processNewImagePair, verbatim from EST.cpp:263-315 (octave 0).
+// Returns the number of processNewImagePair calls made (>= 1); throws std::runtime_error where the reference throws.
+struct TAdaptiveThOptions { bool orb_adaptive_fast_th = true; int adaptive_th_min_matches = 100; int detect_fast_th = 20; };   // kitti.ini:113-115
+int processWithAdaptiveThresholds(rso::CStereoOdometryEstimator& vo, rso::CStereoOdometryEstimator::TStereoOdometryRequest& request,
+                                  rso::CStereoOdometryEstimator::TStereoOdometryResult& result, const TAdaptiveThOptions& opt);
+
 struct TStereoCameraParams { double cul, cvl, fl, cur, fr, baseline; };
 struct TObservation { size_t feat_id; float lx, ly, rx, ry; double X, Y, Z; };
 // UTL.h:558-574 (without the camera_pose_on_robot composition, which needs MRPT's CPose3DRotVec).

@@ -1,12 +1,15 @@
 // host_test.cpp -- drives the C++ adapter classes the way CSRBAStereoSLAMEstimator::performStereoSLAM does
 // (EST.cpp:82-216, 220-926) on raw frames written by the test-suite, and dumps what the reference would see.
-//   host_test <frames.bin> <W> <H> <nframes> <nlevels> <nfeats> <voc.yml[.gz]|-> <out.bin>
+//   host_test <frames.bin> <W> <H> <nframes> <nlevels> <nfeats> <voc.yml[.gz]|-> <out.bin> [adaptive_min_matches]
+// With the optional last argument the frames go through the reference's adaptive threshold loop (EST.cpp:263-315)
+// and every frame's record is prefixed by {calls, fast_th, orb_th}.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <vector>
 #include "CBoWManager.h"
+#include "da_filters.h"
 
 template <typename T> static void put(std::ofstream& o, const T& v) { o.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
 
@@ -23,6 +26,8 @@ int main(int argc, char** argv)
     vo.params_detect.initial_FAST_threshold = 20; vo.params_detect.orb_nlevels = atoi(argv[5]); vo.params_detect.orb_nfeats = atoi(argv[6]);
     vo.setFASTThreshold(20); vo.setORBThreshold(60);
     CBoWManager bow; bool have_voc = std::string(argv[7]) != "-";
+    const int adaptive = argc > 9 ? atoi(argv[9]) : 0;
+    TAdaptiveThOptions aopt; aopt.adaptive_th_min_matches = adaptive; aopt.detect_fast_th = 20;
     t_vector_kf keyframes;
     std::ofstream out(argv[8], std::ios::binary);
     rso::CStereoOdometryEstimator::TStereoOdometryRequest req; rso::CStereoOdometryEstimator::TStereoOdometryResult res;
@@ -30,7 +35,10 @@ int main(int argc, char** argv)
         req.stereo_imgs.reset(new rso::CObservationStereoImages());
         req.stereo_imgs->imageLeft = &frames[(size_t)(2 * k) * W * H]; req.stereo_imgs->imageRight = &frames[(size_t)(2 * k + 1) * W * H];
         req.stereo_imgs->width = W; req.stereo_imgs->height = H; req.stereo_imgs->stride = W; req.repeat = false;
-        if (!vo.processNewImagePair(req, res)) { fprintf(stderr, "frame %d invalid: %s\n", k, vo.lastError().c_str()); }
+        if (adaptive) {
+            const int calls = processWithAdaptiveThresholds(vo, req, res, aopt);
+            put(out, (int32_t)calls); put(out, (int32_t)vo.getFASTThreshold()); put(out, (int32_t)vo.getORBThreshold());
+        } else if (!vo.processNewImagePair(req, res)) { fprintf(stderr, "frame %d invalid: %s\n", k, vo.lastError().c_str()); }
         if (k == 0) { vo.setThisFrameAsKF(); if (have_voc) bow.loadVocabulary(vo.context(), argv[7]); }
         keyframes.push_back(CStereoSLAMKF());
         CStereoSLAMKF& kf = keyframes.back();

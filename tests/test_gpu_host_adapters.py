@@ -86,3 +86,48 @@ def test_adapters_follow_the_reference_call_sequence(tmp_path, voc):
         odb.append(orc.bow_vector(voc, w_, wt_))
         prev = (cur, exp_ids)
     assert off == len(data)
+
+
+def test_adaptive_threshold_loop(tmp_path):
+    """The reference's adaptive FAST/ORB threshold loop (EST.cpp:263-315) driven through the C++ adapters on low-contrast
+    frames, against the same loop replayed in Python on top of the oracle."""
+    from srba_stereo_slam_b200 import frontend, synth
+    from oracle import oracle as orc
+    W, H, NF, NL, NFEAT, MINM = 640, 192, 4, 4, 300, 100
+    frames = synth.CorridorScene(seed=6, width=W, height=H).sequence(NF)
+    frames[1] = (frames[1].astype(np.float32) * 0.35 + 80).astype(np.uint8)     # low contrast: few corners at FAST 20
+    frames[2] = (frames[2].astype(np.float32) * 0.2 + 100).astype(np.uint8)
+    fb = tmp_path / "frames.bin"; frames.tofile(fb)
+    ob = tmp_path / "out.bin"
+    r = subprocess.run([os.path.join(HOST, "host_test"), str(fb), str(W), str(H), str(NF), str(NL), str(NFEAT), "-", str(ob), str(MINM)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(ob, "rb").read(); off = 0
+    fast_th, orb_th = 20, 60                          # adapter defaults: fast 5..30, orb 30..100 (example.ini:15-16,45-46)
+    seen_repeat = False
+    for k in range(NF):
+        calls, f_th, o_th = struct.unpack_from("3i", data, off); off += 12
+        nl, nr, nm, tracked, nq, nda = struct.unpack_from("6i", data, off); off += 24
+        off += 28 * nl + 28 * nr + 32 * nl + 32 * nr + 16 * nm + 8 * nm + 12 * nq + 16 * nda
+        # ---- replay
+        ecalls = 0
+        while True:
+            ol, odl, _ = orc.orb_extract(frames[k, 0], nfeatures=NFEAT, nlevels=NL, fast_threshold=fast_th)
+            orr, odr, _ = orc.orb_extract(frames[k, 1], nfeatures=NFEAT, nlevels=NL, fast_threshold=fast_th)
+            m = len(orc.match_rowband(ol, odl, orr, odr, max_dist=orb_th)); ecalls += 1
+            repeat = False
+            if m < MINM:
+                if fast_th > 5: fast_th = max(5, min(30, max(0, fast_th - 10))); repeat = True
+                elif orb_th < 100: orb_th = min(100, orb_th + 10); repeat = True
+                elif m >= 8: pass
+                else: raise AssertionError("would abort")
+            elif m < MINM * 1.2:
+                if fast_th > 5: fast_th = max(5, fast_th - 5)
+                elif orb_th < 100: orb_th = min(100, orb_th + 5)
+            else:
+                fast_th = min(20, fast_th + 5); orb_th = 60
+            if not repeat:
+                break
+        seen_repeat |= ecalls > 1
+        assert (calls, f_th, o_th, nm) == (ecalls, fast_th, orb_th, m), k
+    assert off == len(data) and seen_repeat
