@@ -24,11 +24,11 @@ struct BfPair { int q_start, nq, t_start, nt, out_start; };
 
 struct sfe_kfdb {
     sfe_context* ctx = nullptr; sfe_bow* bow = nullptr;
-    int cap_frames = 0, stride = 0, B = 0, n_frames = 0, nwords = 0, bm_words = 0;
+    int cap_frames = 0, stride = 0, B = 0, n_frames = 0, nwords = 0, ntiles = 0;
     uint8_t* d_msub = nullptr; int32_t* d_msub_n = nullptr;
     int32_t* d_dbw = nullptr; double* d_dbv = nullptr; int32_t* d_dbn = nullptr;
     int32_t* d_word = nullptr; double* d_weight = nullptr;
-    uint32_t* d_bitmap = nullptr; double* d_dense = nullptr;
+    uint32_t* d_tmask = nullptr; double* d_dense = nullptr;      // [ntiles][nwords] word-major query masks; [B][nwords] dense query vectors
     double* d_score = nullptr; int32_t* d_common = nullptr;
     int32_t* d_qid = nullptr; double* d_qscore = nullptr; int32_t* d_qn = nullptr;
     BfPair* d_pairs = nullptr; int32_t* d_pair_kf = nullptr; uint32_t* d_best = nullptr;
@@ -165,62 +165,69 @@ kf_vector_kernel(const int32_t* __restrict__ word, const double* __restrict__ we
     if (norm > 0.0) for (int i = tid; i < m; i += KV_THREADS) out_v[i] = out_v[i] / norm;
 }
 
-// ---- 4. query side: bitmap + dense vector of each pair's BoW vector (and the inverse, to clean up) -------------
+// ---- 4. query side: per 32-query tile a word-major hit mask T[tile][word] (bit q = query q of the tile contains the
+//         word) + the dense vector of each pair's BoW vector (and the inverse, to clean up) -----------------------
 __global__ void kf_query_prep_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn,
-                                     int cap, int base, int nwords, int bm_words, uint32_t* __restrict__ bitmap,
-                                     double* __restrict__ dense, int clear)
+                                     int cap, int base, int nwords, uint32_t* __restrict__ tmask, double* __restrict__ dense, int clear)
 {
     const int p = blockIdx.y, e = base + p;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dbn[e]) return;
     const int w = dbw[(size_t)e * cap + i];
-    if (clear) { dense[(size_t)p * nwords + w] = 0.0; bitmap[(size_t)p * bm_words + (w >> 5)] = 0u; }
-    else { dense[(size_t)p * nwords + w] = dbv[(size_t)e * cap + i]; atomicOr(&bitmap[(size_t)p * bm_words + (w >> 5)], 1u << (w & 31)); }
+    uint32_t* t = tmask + (size_t)(p >> 5) * nwords + w;
+    if (clear) { dense[(size_t)p * nwords + w] = 0.0; *t = 0u; }
+    else { dense[(size_t)p * nwords + w] = dbv[(size_t)e * cap + i]; atomicOr(t, 1u << (p & 31)); }
 }
 
-// ---- 5. exact L1 scores: lane = query (32 per CTA, bitmaps in shared memory), warp = database entry ------------
-// A warp stages the entry's sorted word list in shared memory with coalesced loads (all in flight at once), then
-// every lane walks it (broadcast LDS) testing its own query bitmap; on the ~2 % hits it gathers the query value
-// from the dense vector and accumulates in ascending word order = DBoW2's order (FP64, bit-identical).
-#define KS_WARPS 16
-#define KS_CHUNK 256
-#define KS_HQ 32                  // per-lane hit queue depth (a lane averages ~12 hits per entry)
+// ---- 5. exact L1 scores: lane = query (32 per CTA), warp = database entry ------------------------------------------
+// Word-major hit masks per tile: ONE lookup T[w] tells which of the 32 queries contain word w.  A warp reads 32 consecutive words of the entry (coalesced), looks their masks up, transposes the 32x32 bit
+// matrix across the lanes (5 shuffle stages) so that lane q holds query q's hits in ascending word order, queues them,
+// and drains the queues together: the gathers of a group of hits are issued at once, the FP64 accumulation stays in
+// ascending word order = DBoW2's order (bit-identical scores).
+#define KS_WARPS 8
+#define KS_HQ 36                  // per-lane hit queue depth (a chunk of 32 words adds at most 32 hits)
 
-// Drains a lane's hit queue: the gathers of a group of 4 hits are issued together (memory-level parallelism),
-// the accumulation stays in queue (= ascending word) order.
 __device__ __forceinline__ double ks_flush(const uint32_t* hq, int cnt, const double* __restrict__ myq,
                                            const double* __restrict__ ev, double s)
 {
-    for (int t = 0; t < cnt; t += 4) {
-        uint32_t h[4]; double qv[4], d[4];
+    // groups of 8 hits: 16 independent gathers in flight per lane, then the in-order accumulation
+    for (int t = 0; t < cnt; t += 8) {
+        uint32_t h[8]; double qv[8], d[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = t + k < cnt ? hq[(t + k) * 32] : 0u;
+        for (int k = 0; k < 8; ++k) h[k] = t + k < cnt ? hq[(t + k) * 32] : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { qv[k] = t + k < cnt ? myq[h[k] >> 16] : 0.0; d[k] = t + k < cnt ? __ldg(ev + (h[k] & 0xffffu)) : 0.0; }
+        for (int k = 0; k < 8; ++k) { qv[k] = t + k < cnt ? myq[h[k] >> 16] : 0.0; d[k] = t + k < cnt ? __ldg(ev + (h[k] & 0xffffu)) : 0.0; }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (t + k < cnt) s += fabs(qv[k] - d[k]) - fabs(qv[k]) - fabs(d[k]);
+        for (int k = 0; k < 8; ++k) if (t + k < cnt) s += fabs(qv[k] - d[k]) - fabs(qv[k]) - fabs(d[k]);
     }
     return s;
 }
 
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)      // out[q] bit i = in[i] bit q
+{
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? (((y >> j) & m) | (x & ~m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
+}
+
 __global__ void __launch_bounds__(KS_WARPS * 32)
 kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn, int cap,
-                int base, int nq, int nwords, int bm_words, const uint32_t* __restrict__ bitmap, const double* __restrict__ dense,
+                int base, int nq, int nwords, const uint32_t* __restrict__ tmask, const double* __restrict__ dense,
                 int score_stride, double* __restrict__ score, int32_t* __restrict__ common)
 {
-    extern __shared__ uint32_t bm[];            // [KF_QT][bm_words] | word staging [KS_WARPS][KS_CHUNK] | hit queues [KS_WARPS][KS_HQ][32]
+    extern __shared__ uint32_t sm[];            // hit queues [KS_WARPS][KS_HQ][32]
     const int q0 = blockIdx.y * KF_QT;
     const int nqt = min(KF_QT, nq - q0);
-    for (int i = threadIdx.x; i < KF_QT * bm_words; i += blockDim.x) {
-        const int q = i / bm_words;
-        bm[i] = q < nqt ? bitmap[(size_t)(q0 + q) * bm_words + (i - q * bm_words)] : 0u;
-    }
-    __syncthreads();
+    // The tile's word-major masks (129 KB) stay in global memory: they are L1/L2 resident and leaving shared memory
+    // to the queues lets 6 CTAs (48 warps) share an SM, which is what hides the gather latency.
+    const uint32_t* __restrict__ T = tmask + (size_t)blockIdx.y * nwords;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int* wbuf = reinterpret_cast<int*>(bm + KF_QT * bm_words) + warp * KS_CHUNK;
-    uint32_t* hq = bm + KF_QT * bm_words + KS_WARPS * KS_CHUNK + warp * KS_HQ * 32 + lane;     // slot-major: conflict-free
+    uint32_t* hq = sm + warp * KS_HQ * 32 + lane;                           // slot-major: conflict-free
     const int q = q0 + lane;
-    const uint32_t* mybm = bm + lane * bm_words;           // bm_words is odd -> the 32 lanes hit 32 different banks
     const double* myq = dense + (size_t)min(q, nq - 1) * nwords;
     const int e_end = base + q0 + nqt - 1;                 // the newest query of the tile sees entries < e_end
     for (int e = blockIdx.x * KS_WARPS + warp; e < e_end; e += gridDim.x * KS_WARPS) {
@@ -228,27 +235,18 @@ kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv,
         const int32_t* ew = dbw + (size_t)e * cap;
         const double* ev = dbv + (size_t)e * cap;
         double s = 0.0; int any = 0, cnt = 0;
-        for (int c0 = 0; c0 < n; c0 += KS_CHUNK) {
-            const int m = min(KS_CHUNK, n - c0);
-            __syncwarp();
-#pragma unroll 4
-            for (int i = lane; i < m; i += 32) wbuf[i] = __ldg(ew + c0 + i);
-            __syncwarp();
-            // pad the staged chunk with a word no query contains is not possible (all words may occur), so the tail
-            // of the last group is masked by index instead
-            for (int i = 0; i < m; i += 4) {
-                const int4 w = *reinterpret_cast<const int4*>(wbuf + i);
-                const int ws[4] = { w.x, w.y, w.z, w.w };
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // branch-free push: always store to the current slot, advance only on a hit
-                    const uint32_t hit = (i + k < m) ? ((mybm[ws[k] >> 5] >> (ws[k] & 31)) & 1u) : 0u;
-                    hq[cnt * 32] = ((uint32_t)ws[k] << 16) | (uint32_t)(c0 + i + k);
-                    cnt += (int)hit;
-                }
-                if (__any_sync(0xffffffffu, cnt > KS_HQ - 5)) {      // warp-uniform drain: every lane flushes what it has
-                    if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; cnt = 0; }
-                }
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int i = c0 + lane;
+            const int w = i < n ? __ldg(ew + i) : 0;
+            const uint32_t m = i < n ? __ldg(T + w) : 0u;                   // which queries contain word w
+            uint32_t tm = transpose32(m, lane);                             // lane q: which of the 32 words hit query q
+            if (__any_sync(0xffffffffu, cnt + __popc(tm) > KS_HQ)) {        // warp-uniform drain before the queue could overflow
+                if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; cnt = 0; }
+            }
+            while (__any_sync(0xffffffffu, tm != 0u)) {                      // ascending word order within the chunk
+                const int src = tm ? __ffs(tm) - 1 : 0;
+                const int ws = __shfl_sync(0xffffffffu, w, src);
+                if (tm) { hq[cnt * 32] = ((uint32_t)ws << 16) | (uint32_t)(c0 + src); ++cnt; tm &= tm - 1; }
             }
         }
         if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; }
@@ -351,7 +349,7 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     if (!ctx || !bow || !out || capacity_frames < 1 || capacity_frames > (1 << 20)) return SFE_ERR_INVALID;
     sfe_kfdb* d = new sfe_kfdb(); d->ctx = ctx; d->bow = bow;
     d->cap_frames = capacity_frames; d->stride = ctx->pack.kp_cap; d->B = ctx->cfg.max_pairs;
-    d->nwords = bow->nwords; d->bm_words = (bow->nwords + 31) / 32;
+    d->nwords = bow->nwords; d->ntiles = (ctx->cfg.max_pairs + KF_QT - 1) / KF_QT;
     const size_t F = capacity_frames, S = d->stride, B = d->B;
     cudaError_t e = cudaSuccess;
     auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -359,7 +357,7 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     al((void**)&d->d_msub, F * S * 32); al((void**)&d->d_msub_n, F * 4);
     al((void**)&d->d_dbw, F * S * 4); al((void**)&d->d_dbv, F * S * 8); al((void**)&d->d_dbn, F * 4);
     al((void**)&d->d_word, B * S * 4); al((void**)&d->d_weight, B * S * 8);
-    al((void**)&d->d_bitmap, B * d->bm_words * 4); al((void**)&d->d_dense, B * (size_t)d->nwords * 8);
+    al((void**)&d->d_tmask, (size_t)d->ntiles * d->nwords * 4); al((void**)&d->d_dense, B * (size_t)d->nwords * 8);
     al((void**)&d->d_score, B * F * 8); al((void**)&d->d_common, B * F * 4);
     al((void**)&d->d_qid, B * 4 * 4); al((void**)&d->d_qscore, B * 4 * 8); al((void**)&d->d_qn, B * 4);
     al((void**)&d->d_pairs, B * KF_PAIRS * sizeof(BfPair)); al((void**)&d->d_pair_kf, B * KF_PAIRS * 4);
@@ -367,13 +365,13 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     ah((void**)&d->h_qid, B * 4 * 4); ah((void**)&d->h_qscore, B * 4 * 8); ah((void**)&d->h_qn, B * 4);
     ah((void**)&d->h_pair_kf, B * KF_PAIRS * 4); ah((void**)&d->h_best, B * KF_PAIRS * S * 4); ah((void**)&d->h_msub_n, B * 4);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMemset(d->d_bitmap, 0, B * d->bm_words * 4);
+    if (e == cudaSuccess) e = cudaMemset(d->d_tmask, 0, (size_t)d->ntiles * d->nwords * 4);
     if (e == cudaSuccess) e = cudaMemset(d->d_dense, 0, B * (size_t)d->nwords * 8);
     if (e == cudaSuccess) e = cudaMemset(d->d_msub_n, 0, F * 4);
     if (e == cudaSuccess) e = cudaMemset(d->d_dbn, 0, F * 4);
     if (e != cudaSuccess) { ctx->err = std::string("sfe_kfdb_create: ") + cudaGetErrorString(e); sfe_kfdb_destroy(d); return SFE_ERR_CUDA; }
     cudaFuncSetAttribute(kf_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
-    cudaFuncSetAttribute(kf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KF_QT * d->bm_words * 4 + KS_WARPS * (KS_CHUNK + KS_HQ * 32) * 4);
+    cudaFuncSetAttribute(kf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KS_WARPS * KS_HQ * 32 * 4);
     cudaGetLastError();
     *out = d;
     return SFE_OK;
@@ -383,7 +381,7 @@ extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
 {
     if (!d) return;
     cudaFree(d->d_msub); cudaFree(d->d_msub_n); cudaFree(d->d_dbw); cudaFree(d->d_dbv); cudaFree(d->d_dbn);
-    cudaFree(d->d_word); cudaFree(d->d_weight); cudaFree(d->d_bitmap); cudaFree(d->d_dense); cudaFree(d->d_score);
+    cudaFree(d->d_word); cudaFree(d->d_weight); cudaFree(d->d_tmask); cudaFree(d->d_dense); cudaFree(d->d_score);
     cudaFree(d->d_common); cudaFree(d->d_qid); cudaFree(d->d_qscore); cudaFree(d->d_qn); cudaFree(d->d_pairs);
     cudaFree(d->d_pair_kf); cudaFree(d->d_best);
     cudaFreeHost(d->h_qid); cudaFreeHost(d->h_qscore); cudaFreeHost(d->h_qn); cudaFreeHost(d->h_pair_kf); cudaFreeHost(d->h_best);
@@ -423,16 +421,16 @@ extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs
     if (np2 > 32768) { c->err = "keypoint capacity too large for the BoW vector kernel"; return SFE_ERR_INVALID; }
     kf_vector_kernel<<<npairs, KV_THREADS, (size_t)np2 * 4, s>>>(d->d_word, d->d_weight, c->d_kp_count, cap, np2, base, d->d_dbw, d->d_dbv, d->d_dbn);
     // 4-6. query: every frame against the entries older than itself
-    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, 0);
+    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->d_tmask, d->d_dense, 0);
     const int ne_vis = E - 1;                                   // entries any query of this batch can see
     if (ne_vis > 0) {
         const int tiles = (npairs + KF_QT - 1) / KF_QT;
-        const int gx = std::max(1, std::min((ne_vis + KS_WARPS - 1) / KS_WARPS, (148 + tiles - 1) / tiles));   // one CTA per SM (129 KB of bitmaps each)
-        kf_score_kernel<<<dim3(gx, tiles), KS_WARPS * 32, (size_t)KF_QT * d->bm_words * 4 + (size_t)KS_WARPS * (KS_CHUNK + KS_HQ * 32) * 4, s>>>(
-            d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, d->cap_frames, d->d_score, d->d_common);
+        const int gx = std::max(1, std::min((ne_vis + KS_WARPS - 1) / KS_WARPS, (148 * 6 + tiles - 1) / tiles));   // ~6 CTAs per SM
+        kf_score_kernel<<<dim3(gx, tiles), KS_WARPS * 32, (size_t)KS_WARPS * KS_HQ * 32 * 4, s>>>(
+            d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->d_tmask, d->d_dense, d->cap_frames, d->d_score, d->d_common);
     }
     kf_topk_kernel<<<npairs, 256, 0, s>>>(d->d_score, d->d_common, base, d->cap_frames, 4, d->d_qid, d->d_qscore, d->d_qn);
-    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->bm_words, d->d_bitmap, d->d_dense, 1);
+    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->d_tmask, d->d_dense, 1);
     // 7-8. data association: previous keyframe + BoW hits
     kf_pairs_kernel<<<(npairs * KF_PAIRS + 127) / 128, 128, 0, s>>>(d->d_qid, d->d_qn, d->d_msub_n, base, npairs, cap, d->d_pairs, d->d_pair_kf);
     KF_CUDA(d, cudaMemsetAsync(d->d_best, 0xff, (size_t)npairs * KF_PAIRS * cap * 4, s));
