@@ -334,6 +334,37 @@ def main():
     single = {"ms_per_pair_median": float(np.median(lat[5:])), "frames_per_s": 1e3 / float(np.median(lat[5:])),
               "note": "sfe_process_stereo + sfe_get_values on pageable host images, synchronous, batch of 1 (the live SLAM loop's shape)"}
 
+    # ---- keyframe-to-keyframe matcher against the POPC pipe (BASELINE metric: "popc-pipe % of peak") --------------
+    from srba_stereo_slam_b200 import loop_closure as lc
+    NQ_M, K_M, NDB_M, NMAX_M = 512, 5, 2048, 500
+    lcm = lc.LoopClosureMatcher(fe, NMAX_M, None)
+    dbc, dbb = lc.synth_keyframe_blocks(NDB_M, NMAX_M, seed=100)
+    rng_m = np.random.default_rng(7)
+    src_m = rng_m.integers(0, NDB_M, NQ_M)
+    qc, qb = lc.synth_keyframe_blocks(NQ_M, NMAX_M, seed=200, planted_from=(dbb, dbc, src_m))
+    cand_m = rng_m.integers(0, NDB_M, (NQ_M, K_M)).astype(np.int32); cand_m[:, 0] = src_m
+    lcm.set_database(dbc, dbb, NDB_M); lcm.upload_queries(qc, qb)
+    pr = lcm.build_pairs(cand_m, "peer")
+    for _ in range(3):
+        lcm.run("peer")
+    fe.synchronize(); fe.timer_start()
+    for _ in range(10):
+        lcm.run("peer")
+    ms_m = fe.timer_stop() / 10
+    dist_evals = float((pr["nq"].astype(np.int64) * pr["nt"].astype(np.int64)).sum())
+    sm_ghz = (clk.get("sm_mhz") or 1900.0) / 1e3 if isinstance(clk, dict) else 1.9
+    POPC_PEAK = 148 * 16 * sm_ghz * 1e9 / 1e12    # measured: 16 POPC/clk/SM (profiles/probes/popc_throughput_probe.cu) x 148 SMs x SM clock under load
+    matcher = {"bound": "popc pipe", "kernel": "bf_pairs_kernel", "ms_per_launch": ms_m,
+               "pairs": int(NQ_M * K_M), "distance_evaluations": dist_evals,
+               "achieved": dist_evals * 8 / (ms_m * 1e-3) / 1e12, "peak": POPC_PEAK, "unit": "T popc32-equivalents/s",
+               "frac": dist_evals * 8 / (ms_m * 1e-3) / 1e12 / POPC_PEAK,
+               "popc_instructions_per_distance": 4,
+               "popc_pipe_busy_frac": dist_evals * 4 / (ms_m * 1e-3) / 1e12 / POPC_PEAK,
+               "note": "256-bit Hamming = 8 popc32 when done naively; the kernel's carry-save adder tree issues 4 POPC + 14 LOP3 per "
+                       "distance, so `frac` can exceed 1 while the pipe itself is `popc_pipe_busy_frac` busy",
+               "workload": "%d query KFs x %d candidates vs %d-KF database, %d descriptors/KF (configs[3] shape, one GPU)" % (NQ_M, K_M, NDB_M, NMAX_M)}
+    lcm.close()
+
     # ---- per-kernel times, live (CUDA events around each stage, direct launches) --------------------------------
     fe.set_profiling(True)
     acc = {}
@@ -395,7 +426,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps, "matches_read_back": nmatch,
                         "h2d_link_GBps_measured": h2d_gbs,
                         "timing": "host wall clock between full synchronisations; 3 contexts pipeline PCIe against kernels"},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "full_frontend": full, "single_pair_latency": single}
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "full_frontend": full, "single_pair_latency": single, "matcher_roofline": matcher}
         print(json.dumps(line))
     fe.close()
     if dist is not None:
