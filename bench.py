@@ -270,11 +270,11 @@ def main():
     # ---- full front-end (BASELINE.json configs[2] shape): + BoW query/add + keyframe store + association -----
     full = None
     voc_path = os.path.join(ROOT, "tests", "golden", "voc_flat.npz")
-    if os.path.exists(voc_path) and not args.no_full and args.config == "b":
+    if os.path.exists(voc_path) and not args.no_full:
         vz = np.load(voc_path)
         voc = {k: (vz[k] if vz[k].ndim else vz[k].item()) for k in vz.files}
         bow = frontend.BowDatabase(fe, voc)
-        cap_frames = 4608                                       # >= KITTI-00's 4541 keyframes
+        cap_frames = 4608 if B >= 64 else 36 * B                # >= KITTI-00's 4541 keyframes at the default batch
         kfdb = frontend.KeyframeDatabase(fe, bow, cap_frames)
         steps_full = min(args.steps, (cap_frames // B) - 4)
         prefill = (cap_frames // B) - steps_full - 1            # untimed batches so the timed ones see a large database
