@@ -28,12 +28,13 @@ __device__ __forceinline__ int row7_dp4a(uint32_t lo4, uint32_t hi4)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, MODE == SFE_BLUR_CV24_FIXED ? 8 : 6)
 blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint8_t* __restrict__ blur)
 {
     __shared__ alignas(128) uint8_t tile[BLUR_BOX_H * BLUR_BOX_W];
     __shared__ alignas(8) uint64_t bar;
-    __shared__ alignas(16) int rowbuf[BLUR_ROWS * BLUR_TW];
+    // fixed point: row sums are <= 255*257 = 65535, so two vertically adjacent rows share a 32-bit word (DP2A operand)
+    __shared__ alignas(16) int rowbuf[(MODE == SFE_BLUR_CV24_FIXED ? BLUR_ROWS / 2 : BLUR_ROWS) * BLUR_TW];
 
     const int tid = threadIdx.x;
     const int4 ti = __ldg(tile_tab + blockIdx.x);
@@ -49,7 +50,10 @@ blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
         mbar_arrive_expect_tx(&bar, BLUR_BOX_H * BLUR_BOX_W);
         tma_load_3d(tile, &P.pyr_map[level], bx0, y0 - 3, img, &bar);
     }
-    mbar_wait(&bar, 0);
+    // one warp polls the mbarrier, the others park in the hardware barrier (a spinning warp burns issue slots that the
+    // co-resident CTAs need: 8.4 M of 298 M warp instructions were try_wait retries)
+    if (tid < 32) mbar_wait(&bar, 0);
+    __syncthreads();
 
     // ---- reflect-101 fix-up, border tiles only (TMA zero-filled what lies outside the image) ----------
     // tile row r <-> image row y0-3+r (r < BLUR_ROWS used); tile byte c <-> image column bx0+c
@@ -75,6 +79,64 @@ blur_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
             }
         }
         __syncthreads();
+    }
+
+    if constexpr (MODE == SFE_BLUR_CV24_FIXED) {
+        // ---- row pass, fixed point: 2 rows x 4 adjacent outputs per thread.  The 7 taps are applied to the ALIGNED words
+        //      with shifted tap patterns (10 DP4A per 4 outputs, no byte permutes); the sums of rows 2p and 2p+1 are packed
+        //      into one word (low | high << 16) for the column pass' DP2A ------------------------------------------------
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile) + 3;      // word 3 = pixels x0-4 .. x0-1
+        auto row4 = [](uint32_t A, uint32_t B, uint32_t C, uint32_t (&o)[4]) {  // A|B|C = pixels x-4..x-1 | x..x+3 | x+4..x+7
+            o[0] = __dp4a(B, 0x12223137u, __dp4a(A, 0x31221200u, 0u));                             // x-3 .. x+3
+            o[1] = __dp4a(C, 0x00000012u, __dp4a(B, 0x22313731u, __dp4a(A, 0x22120000u, 0u)));     // x-2 .. x+4
+            o[2] = __dp4a(C, 0x00001222u, __dp4a(B, 0x31373122u, __dp4a(A, 0x12000000u, 0u)));     // x-1 .. x+5
+            o[3] = __dp4a(C, 0x00122231u, __dp4a(B, 0x37312212u, 0u));                             // x   .. x+6
+        };
+#pragma unroll
+        for (int it = 0; it < ((BLUR_ROWS / 2) * (BLUR_TW / 4) + 255) / 256; ++it) {     // unrolled: tap words stay in registers
+            const int i = tid + 256 * it;
+            if (i >= (BLUR_ROWS / 2) * (BLUR_TW / 4)) break;
+            const int pr = i >> 5, q = i & 31;
+            const uint32_t* c = tw + 2 * pr * (BLUR_BOX_W / 4) + q;
+            uint32_t lo[4], hi[4];
+            row4(c[0], c[1], c[2], lo);
+            row4(c[BLUR_BOX_W / 4], c[BLUR_BOX_W / 4 + 1], c[BLUR_BOX_W / 4 + 2], hi);
+            *reinterpret_cast<uint4*>(rowbuf + pr * BLUR_TW + 4 * q) =
+                make_uint4(__byte_perm(lo[0], hi[0], 0x5410), __byte_perm(lo[1], hi[1], 0x5410),
+                           __byte_perm(lo[2], hi[2], 0x5410), __byte_perm(lo[3], hi[3], 0x5410));
+        }
+        __syncthreads();
+
+        // ---- column pass, fixed point: 4 columns x 4 rows per thread from 5 packed row pairs; 4 DP2A per output (the
+        //      accumulator starts at 2^15), min(s, 2^24-1) so that byte 2 is the saturated result, PRMT packs 4 pixels ----
+        uint8_t* dst = blur + g.lvl_ofs + (size_t)img * g.img_bytes;
+        {
+            const int yq = (tid >> 5) * 4, xq = (tid & 31) * 4;               // (BLUR_TH/4) * (BLUR_TW/4) == 256 items
+            uint4 W[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) W[k] = *reinterpret_cast<const uint4*>(rowbuf + ((yq >> 1) + k) * BLUR_TW + xq);
+            const int nvalid = min(max(w - (x0 + xq), 0), 4);
+            const uint32_t cmask = nvalid >= 4 ? 0xffffffffu : ((1u << (8 * nvalid)) - 1u);     // zero beyond the image width
+            // taps (t_a | t_b << 8) on a pair (row 2j, row 2j+1):  even output rows  (18,34)(49,55)(49,34)(18,0)
+            //                                                      odd output rows   (0,18)(34,49)(55,49)(34,18)
+            auto col = [](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, bool odd) -> uint32_t {
+                uint32_t s = odd ? __dp2a_lo(w3, 0x1222u, __dp2a_lo(w2, 0x3137u, __dp2a_lo(w1, 0x3122u, __dp2a_lo(w0, 0x1200u, 1u << 15))))
+                                 : __dp2a_lo(w3, 0x0012u, __dp2a_lo(w2, 0x2231u, __dp2a_lo(w1, 0x3731u, __dp2a_lo(w0, 0x2212u, 1u << 15))));
+                return min(s, 0x00ffffffu);
+            };
+#pragma unroll
+            for (int yy = 0; yy < 4; ++yy) {
+                if (y0 + yq + yy >= h) break;
+                const int j = yy >> 1; const bool odd = yy & 1;
+                const uint32_t s0 = col(W[j].x, W[j + 1].x, W[j + 2].x, W[j + 3].x, odd);
+                const uint32_t s1 = col(W[j].y, W[j + 1].y, W[j + 2].y, W[j + 3].y, odd);
+                const uint32_t s2 = col(W[j].z, W[j + 1].z, W[j + 2].z, W[j + 3].z, odd);
+                const uint32_t s3 = col(W[j].w, W[j + 1].w, W[j + 2].w, W[j + 3].w, odd);
+                const uint32_t out = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+                *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + yq + yy) * g.pitch + x0 + xq) = out & cmask;
+            }
+        }
+        return;
     }
 
     // ---- row pass: 4 adjacent outputs per thread from 3 aligned words ------------------------------------

@@ -178,6 +178,35 @@ def test_edge_cases(mods):
         frontend.StereoFrontEnd(nlevels=9)
 
 
+@pytest.mark.parametrize("blur_mode", [0, 1])
+def test_saturated_and_odd_sized_images(mods, blur_mode):
+    """Over-exposed blocks (row sums at the 16-bit limit, column sums above 2^24: the blur's saturation path), hard
+    black/white edges on the image border (reflect-101 halo) and an odd size that leaves partial tiles on every level."""
+    frontend, orc = mods
+    W, H = 413, 287
+    rng = np.random.default_rng(11)
+    img = np.zeros((H, W), np.uint8)
+    img[:, :] = (rng.random((H, W)) * 2).astype(np.uint8) + 254              # 254/255 everywhere
+    img[40:120, 60:200] = (rng.random((80, 140)) * 255).astype(np.uint8)     # a textured patch
+    img[150:, :30] = 0; img[:25, 300:] = 0; img[260:, 380:] = 255            # blocks touching the borders
+    img[200:240, 100:300:2] = 0                                              # 1-pixel stripes
+    fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=5, nfeatures=300, max_pairs=1, blur_mode=blur_mode)
+    try:
+        fe.process_stereo(img, img[::-1].copy())
+        for s, im in enumerate((img, img[::-1].copy())):
+            ok, od, ex = orc.orb_extract(im, nfeatures=300, nlevels=5, fast_threshold=20, want_levels=True, blur_mode=blur_mode)
+            for l in range(5):
+                assert np.array_equal(fe.get_level(s, l), ex["pyramid"][l]), ("pyramid", s, l)
+                assert np.array_equal(fe.get_level(s, l, blurred=True), ex["blurred"][l]), ("blur", s, l)
+            assert ex["blurred"][0].max() == 255
+            kl, kr, dl, dr, m = fe.get_values(0)
+            gk, gd = (kl, dl) if s == 0 else (kr, dr)
+            _assert_keypoints_equal(gk, ok)
+            assert np.array_equal(gd, od)
+    finally:
+        fe.close()
+
+
 def test_match_bf(mods, golden):
     """cv::BFMatcher(NORM_HAMMING,false).match (EST.cpp:1447-1452): golden vectors + oracle at 1000x1000 and ragged sizes."""
     frontend, orc = mods
