@@ -6,11 +6,12 @@
 // EST.cpp:112,267).  The outputs are what voEngine.getValues hands to CStereoSLAMKF
 // (reference CStereoSLAMKF.h:68-70,99-104): 28-byte keypoints and N x 32 CV_8U descriptors.
 //
-// One warp per keypoint slot.  Orientation: lanes = patch columns, 31 coalesced row reads from the
-// UNBLURRED level, integer moments reduced with warp shuffles (exact), then OpenCV's fastAtan2
-// polynomial evaluated unfused.  Descriptor: the 37x37 BLURRED patch is staged in shared memory,
-// each lane evaluates 8 of the 256 tests (one descriptor byte) with the pattern rotated in float,
-// unfused, round-half-even -- bit-identical to the CPU arithmetic.
+// One warp per keypoint slot.  Both patches are staged with 8-byte cp.async copies of 8-byte aligned spans (5-6 lanes per
+// row): the 31-row UNBLURRED patch for the orientation and the 37-row BLURRED patch for the tests.  Orientation: lane =
+// patch row; the row's 32 aligned bytes are masked to the radius-15 disc and reduced with DP4A (weights 1 and u), the
+// integer moments are exact; OpenCV's fastAtan2 polynomial is evaluated unfused.  Descriptor: each lane evaluates 8 of
+// the 256 tests (one descriptor byte) with the pattern rotated in float, unfused, round-half-even through the
+// 1.5*2^23 magic add (bit-identical to cvRound of the CPU arithmetic); the biased integers index shared memory directly.
 #include "sfe_internal.cuh"
 
 __device__ const int8_t d_brief_pattern[256 * 4] = {
@@ -20,7 +21,35 @@ __constant__ int c_umax[16] = { 15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 
 
 #define DESC_WARPS 8
 #define PATCH_R 18
-#define PATCH_PITCH 44      // 11 words: the 37-byte row plus up to 3 bytes of alignment slack on the left
+#define BP_ROWS (2 * PATCH_R + 1)   // blurred patch: 37 rows, 48 bytes copied (37 + 7 bytes of alignment slack <= 44) into a
+#define BP_PITCH 56                 // 14-word pitch: the random test gathers spread over 16 bank offsets
+#define OP_ROWS 31                  // orientation patch: 31 rows of 40 bytes (31 + 7 <= 38)
+#define OP_PITCH 40
+
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)     // unsigned pixels x signed weights
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
+    return d;
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, so all copies of a lane are in flight at once
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// weights u = 4k + b - 15 of the four bytes of aligned word k, as packed int8
+__host__ __device__ constexpr uint32_t orient_wu(int k)
+{
+    return ((uint32_t)(uint8_t)(int8_t)(4 * k - 15)) | ((uint32_t)(uint8_t)(int8_t)(4 * k - 14) << 8) |
+           ((uint32_t)(uint8_t)(int8_t)(4 * k - 13) << 16) | ((uint32_t)(uint8_t)(int8_t)(4 * k - 12) << 24);
+}
 
 __device__ __forceinline__ float cv_fast_atan2(float y, float x)
 {
@@ -51,90 +80,111 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
                 const int32_t* __restrict__ sel_count,
                 sfe_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ kp_count)
 {
-    __shared__ uint32_t pat_s[256];                                   // [test-in-byte j][lane] -> char4
-    __shared__ alignas(16) uint8_t patch_s[DESC_WARPS][(2 * PATCH_R + 1) * PATCH_PITCH];
+    __shared__ uint32_t pat_s[256];                                   // [test-in-byte j][lane] -> packed int8 (ax, ay, bx, by)
+    __shared__ uint32_t disc_mask[16 * 9];                            // [|v|][aligned word k], pitch 9: conflict-free
+    __shared__ alignas(16) uint8_t bpatch[DESC_WARPS][BP_ROWS * BP_PITCH];
+    __shared__ alignas(16) uint8_t opatch[DESC_WARPS][OP_ROWS * OP_PITCH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
-    {   // pattern entry t = 8*L + j  ->  pat_s[j*32 + L]
-        const uint32_t e = reinterpret_cast<const uint32_t*>(d_brief_pattern)[tid];
-        pat_s[(tid & 7) * 32 + (tid >> 3)] = e;
+    {   // pattern entry t = 8*L + j  ->  pat_s[j*32 + L] (the strided side is the cached global read)
+        pat_s[tid] = reinterpret_cast<const uint32_t*>(d_brief_pattern)[8 * (tid & 31) + (tid >> 5)];
+        if (tid < 128) {                                              // byte masks of the radius-15 disc: |u| <= umax[|v|]
+            const int av = tid >> 3, k = tid & 7, m = c_umax[av];
+            uint32_t mk = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) if (abs(4 * k + b - 15) <= m) mk |= 0xffu << (8 * b);
+            disc_mask[av * 9 + k] = mk;
+        }
     }
     __syncthreads();
 
-    // slot -> (level, index)
+    // slot -> (level, index): lanes 0..7 hold the per-level counts, an 8-lane scan gives the level boundaries
     const int slot = blockIdx.x * DESC_WARPS + warp;
-    int level = -1, idx = 0, cum = 0;
-    for (int l = 0; l < P.nlevels; ++l) {
-        const int c = sel_count[(size_t)img * P.nlevels + l];
-        if (level < 0 && slot < cum + c) { level = l; idx = slot - cum; }
-        cum += c;
-    }
-    if (blockIdx.x == 0 && tid == 0) kp_count[img] = cum;
-    if (level < 0) return;
+    const int cnt = lane < P.nlevels ? sel_count[(size_t)img * P.nlevels + lane] : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    const uint32_t below = __ballot_sync(0xffffffffu, lane < P.nlevels && slot < inc);
+    if (blockIdx.x == 0 && tid == 7) kp_count[img] = inc;            // lane 7: total over all levels (SFE_MAX_LEVELS == 8)
+    if (below == 0u) return;                                          // warp-uniform
+    const int level = __ffs(below) - 1;
+    const int idx = slot - (__shfl_sync(0xffffffffu, inc, level) - __shfl_sync(0xffffffffu, cnt, level));
 
     const LevelGeom& g = P.g[level];
     const size_t so = (size_t)img * P.sel_img_stride + g.sel_ofs + idx;
     const uint32_t xy = sel_xy[so];
     const int x = xy & 0xffff, y = xy >> 16;
     const size_t lofs = g.lvl_ofs + (size_t)img * g.img_bytes;
-    const uint8_t* im = pyr + lofs;
-    const uint8_t* bl = blur + lofs;
-    const int pitch = g.pitch;
+    const int pitch = g.pitch;                                        // multiple of 128: aligned spans stay inside the row
 
-    // ---- orientation: m10 = sum u*I, m01 = sum v*I over the radius-15 disc ------------------
-    // lane = column u; the disc is symmetric (umax[umax[v]] >= v), so column u spans rows |v| <= umax[|u|]
-    int m10 = 0, m01 = 0;
+    // ---- stage both patches: 8-byte aligned spans, one 8-byte cp.async per lane and step ------------------------------
+    uint8_t* op = opatch[warp];
+    uint8_t* bp = bpatch[warp];
+    const int xo = (x - 15) & ~7, osh = (x - 15) - xo;               // orientation patch: columns x-15 .. x+15
+    const int xb = (x - PATCH_R) & ~7, bsh = (x - PATCH_R) - xb;     // blurred patch: columns x-18 .. x+18
     {
-        const int u = lane - 15;
-        const int vm = lane < 31 ? c_umax[abs(u)] : -1;
-        const uint8_t* p = im + (size_t)(y - 15) * pitch + x + u;
-        int sum = 0;
+        const int sub = lane / 5, part = lane - 5 * sub;              // 6 rows x 5 pieces per step (lanes 30, 31 idle)
+        const uint8_t* src = pyr + lofs + (size_t)(y - 15 + sub) * pitch + xo + 8 * part;
+        uint8_t* dst = op + sub * OP_PITCH + 8 * part;
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) {
-            if (abs(v) <= vm) { const int I = __ldg(p); sum += I; m01 += v * I; }
-            p += pitch;
-        }
-        m10 = u * sum;
+        for (int k = 0; k < 6; ++k)
+            if (lane < 30 && sub + 6 * k < OP_ROWS) cp_async8(dst + 6 * k * OP_PITCH, src + (size_t)(6 * k) * pitch);
+    }
+    {
+        const int sub = lane / 6, part = lane - 6 * sub;              // 5 rows x 6 pieces per step (lanes 30, 31 idle)
+        const uint8_t* src = blur + lofs + (size_t)(y - PATCH_R + sub) * pitch + xb + 8 * part;
+        uint8_t* dst = bp + sub * BP_PITCH + 8 * part;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        for (int k = 0; k < 8; ++k)
+            if (lane < 30 && sub + 5 * k < BP_ROWS) cp_async8(dst + 5 * k * BP_PITCH, src + (size_t)(5 * k) * pitch);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- orientation: m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = row v ----------------------------
+    int m10 = 0, m01 = 0;
+    if (lane < OP_ROWS) {
+        const int v = lane - 15;
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(op + lane * OP_PITCH) + (osh >> 2);
+        const uint32_t* mk = disc_mask + abs(v) * 9;
+        const int bs = (osh & 3) * 8;
+        uint32_t w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = rw[k];
+        int s1 = 0, su = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t a = __funnelshift_r(w[k], w[k + 1], bs) & mk[k];      // pixels u = 4k-15 .. 4k-12 of row v
+            s1 = (int)__dp4a(a, 0x01010101u, (uint32_t)s1);
+            su = dp4a_u8_s8(a, orient_wu(k), su);
         }
+        m10 = su; m01 = v * s1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
     }
     const float angle = cv_fast_atan2((float)m01, (float)m10);
-
-    // ---- stage the blurred 37x37 patch with aligned 32-bit loads: 37 rows x 11 words ----------------
-    uint8_t* ps = patch_s[warp];
-    const int xa = (x - PATCH_R) & ~3, xsh = (x - PATCH_R) - xa;
-    {
-        const uint8_t* b0 = bl + (size_t)(y - PATCH_R) * pitch + xa;
-#pragma unroll
-        for (int k = 0; k < 13; ++k) {
-            const int idx = lane + 32 * k;
-            if (idx < (2 * PATCH_R + 1) * 11) {
-                const int row = idx / 11, col = idx - row * 11;
-                reinterpret_cast<uint32_t*>(ps)[row * (PATCH_PITCH / 4) + col] =
-                    __ldg(reinterpret_cast<const uint32_t*>(b0 + (size_t)row * pitch) + col);
-            }
-        }
-    }
-    __syncwarp();
 
     // ---- 256 tests, 8 per lane -------------------------------------------------------------
     const float arad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     const float ca = (float)cos((double)arad), sa = (float)sin((double)arad);
-    const uint8_t* ctr = ps + PATCH_R * PATCH_PITCH + PATCH_R + xsh;
+    // cvRound through the magic add: bits(v + 1.5*2^23) = 0x4B400000 + round_half_even(v); the bias is folded into the base
+    const float MAGIC = 12582912.f;
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(bp) + PATCH_R * BP_PITCH + PATCH_R + bsh - 0x4B400000u * (BP_PITCH + 1u);
     uint32_t byte = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint32_t e = pat_s[j * 32 + lane];
         const float ax = (float)(int8_t)(e & 0xff), ay = (float)(int8_t)((e >> 8) & 0xff);
         const float bx = (float)(int8_t)((e >> 16) & 0xff), by = (float)(int8_t)(e >> 24);
-        const int x0 = __float2int_rn(__fsub_rn(__fmul_rn(ax, ca), __fmul_rn(ay, sa)));
-        const int y0 = __float2int_rn(__fadd_rn(__fmul_rn(ax, sa), __fmul_rn(ay, ca)));
-        const int x1 = __float2int_rn(__fsub_rn(__fmul_rn(bx, ca), __fmul_rn(by, sa)));
-        const int y1 = __float2int_rn(__fadd_rn(__fmul_rn(bx, sa), __fmul_rn(by, ca)));
-        const int t0 = ctr[y0 * PATCH_PITCH + x0], t1 = ctr[y1 * PATCH_PITCH + x1];
+        const float fx0 = __fadd_rn(__fsub_rn(__fmul_rn(ax, ca), __fmul_rn(ay, sa)), MAGIC);
+        const float fy0 = __fadd_rn(__fadd_rn(__fmul_rn(ax, sa), __fmul_rn(ay, ca)), MAGIC);
+        const float fx1 = __fadd_rn(__fsub_rn(__fmul_rn(bx, ca), __fmul_rn(by, sa)), MAGIC);
+        const float fy1 = __fadd_rn(__fadd_rn(__fmul_rn(bx, sa), __fmul_rn(by, ca)), MAGIC);
+        const uint32_t t0 = lds_u8(__float_as_uint(fy0) * BP_PITCH + __float_as_uint(fx0) + cbase);
+        const uint32_t t1 = lds_u8(__float_as_uint(fy1) * BP_PITCH + __float_as_uint(fx1) + cbase);
         byte |= (uint32_t)(t0 < t1) << j;
     }
     // gather 4 bytes per word: lanes 4k..4k+3 -> word k
