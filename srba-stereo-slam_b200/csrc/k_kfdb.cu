@@ -29,7 +29,7 @@ struct sfe_kfdb {
     int32_t* d_dbw = nullptr; double* d_dbv = nullptr; int32_t* d_dbn = nullptr;
     int32_t* d_word = nullptr; double* d_weight = nullptr;
     uint32_t* d_tmask = nullptr; double* d_dense = nullptr;      // [ntiles][nwords] word-major query masks; [B][nwords] dense query vectors
-    double* d_score = nullptr; int32_t* d_common = nullptr;
+    double* d_score = nullptr; int32_t* d_common = nullptr; int* d_work_ctr = nullptr;
     int32_t* d_qid = nullptr; double* d_qscore = nullptr; int32_t* d_qn = nullptr;
     BfPair* d_pairs = nullptr; int32_t* d_pair_kf = nullptr; uint32_t* d_best = nullptr;
     int32_t* h_qid = nullptr; double* h_qscore = nullptr; int32_t* h_qn = nullptr; int32_t* h_pair_kf = nullptr; uint32_t* h_best = nullptr;
@@ -180,28 +180,12 @@ __global__ void kf_query_prep_kernel(const int32_t* __restrict__ dbw, const doub
 }
 
 // ---- 5. exact L1 scores: lane = query (32 per CTA), warp = database entry ------------------------------------------
-// Word-major hit masks per tile: ONE lookup T[w] tells which of the 32 queries contain word w.  A warp reads 32 consecutive words of the entry (coalesced), looks their masks up, transposes the 32x32 bit
-// matrix across the lanes (5 shuffle stages) so that lane q holds query q's hits in ascending word order, queues them,
-// and drains the queues together: the gathers of a group of hits are issued at once, the FP64 accumulation stays in
-// ascending word order = DBoW2's order (bit-identical scores).
+// Word-major hit masks per tile: ONE lookup T[w] tells which of the 32 queries contain word w.  A warp reads 32
+// consecutive words of the entry (coalesced), looks their masks up, transposes the 32x32 bit matrix across the lanes
+// (5 shuffle stages) so that lane q holds query q's hits, then walks the chunk's words in ascending order, four at a
+// time: word id and entry value by shuffle, the query value by one predicated gather, FP64 accumulation in ascending
+// word order = DBoW2's order (bit-identical scores).  No shared memory, no queues.
 #define KS_WARPS 8
-#define KS_HQ 36                  // per-lane hit queue depth (a chunk of 32 words adds at most 32 hits)
-
-__device__ __forceinline__ double ks_flush(const uint32_t* hq, int cnt, const double* __restrict__ myq,
-                                           const double* __restrict__ ev, double s)
-{
-    // groups of 8 hits: 16 independent gathers in flight per lane, then the in-order accumulation
-    for (int t = 0; t < cnt; t += 8) {
-        uint32_t h[8]; double qv[8], d[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) h[k] = t + k < cnt ? hq[(t + k) * 32] : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { qv[k] = t + k < cnt ? myq[h[k] >> 16] : 0.0; d[k] = t + k < cnt ? __ldg(ev + (h[k] & 0xffffu)) : 0.0; }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (t + k < cnt) s += fabs(qv[k] - d[k]) - fabs(qv[k]) - fabs(d[k]);
-    }
-    return s;
-}
 
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)      // out[q] bit i = in[i] bit q
 {
@@ -214,42 +198,60 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)      // ou
     return x;
 }
 
-__global__ void __launch_bounds__(KS_WARPS * 32)
+__global__ void __launch_bounds__(KS_WARPS * 32, 6)
 kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn, int cap,
                 int base, int nq, int nwords, const uint32_t* __restrict__ tmask, const double* __restrict__ dense,
-                int score_stride, double* __restrict__ score, int32_t* __restrict__ common)
+                int score_stride, double* __restrict__ score, int32_t* __restrict__ common, int ntiles, int n_items,
+                int* __restrict__ work_ctr)
 {
-    extern __shared__ uint32_t sm[];            // hit queues [KS_WARPS][KS_HQ][32]
-    const int q0 = blockIdx.y * KF_QT;
-    const int nqt = min(KF_QT, nq - q0);
-    // The tile's word-major masks (129 KB) stay in global memory: they are L1/L2 resident and leaving shared memory
-    // to the queues lets 6 CTAs (48 warps) share an SM, which is what hides the gather latency.
-    const uint32_t* __restrict__ T = tmask + (size_t)blockIdx.y * nwords;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* hq = sm + warp * KS_HQ * 32 + lane;                           // slot-major: conflict-free
-    const int q = q0 + lane;
-    const double* myq = dense + (size_t)min(q, nq - 1) * nwords;
-    const int e_end = base + q0 + nqt - 1;                 // the newest query of the tile sees entries < e_end
-    for (int e = blockIdx.x * KS_WARPS + warp; e < e_end; e += gridDim.x * KS_WARPS) {
+    // Persistent warps pull (entry, query tile) items from a global counter: the items are long (up to cap/32 chunks)
+    // and uneven, a static split lost up to one item per warp to wave quantisation.
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_ctr, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int e = item / ntiles, tile = item - e * ntiles;
+        const int q0 = tile * KF_QT;
+        const int nqt = min(KF_QT, nq - q0);
+        if (e >= base + q0 + nqt - 1) continue;            // the newest query of the tile sees entries < base + q0 + nqt - 1
+        // The tile's word-major masks (4 B per vocabulary word) and the dense query vectors stay in global memory: they
+        // are L1/L2 resident, and a kernel without shared memory keeps 48 warps per SM to hide the gather latency.
+        const uint32_t* __restrict__ T = tmask + (size_t)tile * nwords;
+        const int q = q0 + lane;
+        const double* __restrict__ myq = dense + (size_t)min(q, nq - 1) * nwords;
         const int n = dbn[e];
         const int32_t* ew = dbw + (size_t)e * cap;
         const double* ev = dbv + (size_t)e * cap;
-        double s = 0.0; int any = 0, cnt = 0;
+        double s = 0.0; bool any = false;
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int i = c0 + lane;
-            const int w = i < n ? __ldg(ew + i) : 0;
-            const uint32_t m = i < n ? __ldg(T + w) : 0u;                   // which queries contain word w
-            uint32_t tm = transpose32(m, lane);                             // lane q: which of the 32 words hit query q
-            if (__any_sync(0xffffffffu, cnt + __popc(tm) > KS_HQ)) {        // warp-uniform drain before the queue could overflow
-                if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; cnt = 0; }
-            }
-            while (__any_sync(0xffffffffu, tm != 0u)) {                      // ascending word order within the chunk
-                const int src = tm ? __ffs(tm) - 1 : 0;
-                const int ws = __shfl_sync(0xffffffffu, w, src);
-                if (tm) { hq[cnt * 32] = ((uint32_t)ws << 16) | (uint32_t)(c0 + src); ++cnt; tm &= tm - 1; }
+            int w = 0; double dv = 0.0; uint32_t m = 0u;
+            if (i < n) { w = __ldg(ew + i); dv = __ldg(ev + i); m = __ldg(T + w); }      // m: which queries contain word w
+            const uint32_t tm = transpose32(m, lane);                 // lane q: which of the chunk's 32 words hit query q
+            const uint32_t anyhit = __reduce_or_sync(0xffffffffu, tm);
+            any |= tm != 0u;
+            // words in ascending order (= DBoW2's accumulation order), four at a time: the entry's word id and value come
+            // by shuffle from the lane that loaded them, the query's value is one predicated gather; groups without any
+            // hit in the whole tile are skipped warp-uniformly.  (Prefetching the next chunks' words/masks was measured:
+            // no gain - the exposed latency is in the gathers.)
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                if (((anyhit >> (4 * g)) & 0xfu) == 0u) continue;
+                double qv[4], dj[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = 4 * g + k;
+                    const int wj = __shfl_sync(0xffffffffu, w, j);
+                    dj[k] = __shfl_sync(0xffffffffu, dv, j);
+                    qv[k] = ((tm >> j) & 1u) ? __ldg(myq + wj) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((tm >> (4 * g + k)) & 1u) s += fabs(qv[k] - dj[k]) - fabs(qv[k]) - fabs(dj[k]);
             }
         }
-        if (cnt) { s = ks_flush(hq, cnt, myq, ev, s); any = 1; }
         if (lane < nqt) {
             score[(size_t)q * score_stride + e] = s;
             common[(size_t)q * score_stride + e] = (any && e < base + q) ? 1 : 0;     // a frame only sees older entries
@@ -358,7 +360,7 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     al((void**)&d->d_dbw, F * S * 4); al((void**)&d->d_dbv, F * S * 8); al((void**)&d->d_dbn, F * 4);
     al((void**)&d->d_word, B * S * 4); al((void**)&d->d_weight, B * S * 8);
     al((void**)&d->d_tmask, (size_t)d->ntiles * d->nwords * 4); al((void**)&d->d_dense, B * (size_t)d->nwords * 8);
-    al((void**)&d->d_score, B * F * 8); al((void**)&d->d_common, B * F * 4);
+    al((void**)&d->d_score, B * F * 8); al((void**)&d->d_common, B * F * 4); al((void**)&d->d_work_ctr, 256);
     al((void**)&d->d_qid, B * 4 * 4); al((void**)&d->d_qscore, B * 4 * 8); al((void**)&d->d_qn, B * 4);
     al((void**)&d->d_pairs, B * KF_PAIRS * sizeof(BfPair)); al((void**)&d->d_pair_kf, B * KF_PAIRS * 4);
     al((void**)&d->d_best, B * KF_PAIRS * S * 4);
@@ -371,7 +373,6 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     if (e == cudaSuccess) e = cudaMemset(d->d_dbn, 0, F * 4);
     if (e != cudaSuccess) { ctx->err = std::string("sfe_kfdb_create: ") + cudaGetErrorString(e); sfe_kfdb_destroy(d); return SFE_ERR_CUDA; }
     cudaFuncSetAttribute(kf_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
-    cudaFuncSetAttribute(kf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KS_WARPS * KS_HQ * 32 * 4);
     cudaGetLastError();
     *out = d;
     return SFE_OK;
@@ -382,7 +383,7 @@ extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
     if (!d) return;
     cudaFree(d->d_msub); cudaFree(d->d_msub_n); cudaFree(d->d_dbw); cudaFree(d->d_dbv); cudaFree(d->d_dbn);
     cudaFree(d->d_word); cudaFree(d->d_weight); cudaFree(d->d_tmask); cudaFree(d->d_dense); cudaFree(d->d_score);
-    cudaFree(d->d_common); cudaFree(d->d_qid); cudaFree(d->d_qscore); cudaFree(d->d_qn); cudaFree(d->d_pairs);
+    cudaFree(d->d_common); cudaFree(d->d_work_ctr); cudaFree(d->d_qid); cudaFree(d->d_qscore); cudaFree(d->d_qn); cudaFree(d->d_pairs);
     cudaFree(d->d_pair_kf); cudaFree(d->d_best);
     cudaFreeHost(d->h_qid); cudaFreeHost(d->h_qscore); cudaFreeHost(d->h_qn); cudaFreeHost(d->h_pair_kf); cudaFreeHost(d->h_best);
     cudaFreeHost(d->h_msub_n);
@@ -425,9 +426,11 @@ extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs
     const int ne_vis = E - 1;                                   // entries any query of this batch can see
     if (ne_vis > 0) {
         const int tiles = (npairs + KF_QT - 1) / KF_QT;
-        const int gx = std::max(1, std::min((ne_vis + KS_WARPS - 1) / KS_WARPS, (148 * 6 + tiles - 1) / tiles));   // ~6 CTAs per SM
-        kf_score_kernel<<<dim3(gx, tiles), KS_WARPS * 32, (size_t)KS_WARPS * KS_HQ * 32 * 4, s>>>(
-            d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->d_tmask, d->d_dense, d->cap_frames, d->d_score, d->d_common);
+        const int n_items = ne_vis * tiles;
+        const int gx = std::max(1, std::min((n_items + KS_WARPS - 1) / KS_WARPS, 148 * 6));       // persistent: 6 CTAs per SM
+        KF_CUDA(d, cudaMemsetAsync(d->d_work_ctr, 0, sizeof(int), s));
+        kf_score_kernel<<<gx, KS_WARPS * 32, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->d_tmask, d->d_dense,
+                                                     d->cap_frames, d->d_score, d->d_common, tiles, n_items, d->d_work_ctr);
     }
     kf_topk_kernel<<<npairs, 256, 0, s>>>(d->d_score, d->d_common, base, d->cap_frames, 4, d->d_qid, d->d_qscore, d->d_qn);
     kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->d_tmask, d->d_dense, 1);
