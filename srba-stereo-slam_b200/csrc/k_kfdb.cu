@@ -54,15 +54,15 @@ __device__ __forceinline__ int kf_ham256_csa(const uint4& a0, const uint4& a1, c
 {
     const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
     const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
-    uint32_t t1, s1, t2, s2, t3, s3, f1, tw1, f2, tw2;
+    // four carry-save adders leave two words of weight 1 (s3, x7), one of weight 2 and one of weight 4: 4 POPC like the full
+    // reduction to weights 1/2/4/8, but 16 ALU operations instead of 22 - the ALU pipe (64 lanes/clk/SM), not the POPC pipe
+    // (16 lanes/clk/SM, 4 x 2 cycles), was the longer of the two per distance
+    uint32_t t1, s1, t2, s2, t3, s3, f1, tw1;
     KF_CSA(t1, s1, x0, x1, x2);
     KF_CSA(t2, s2, x3, x4, x5);
     KF_CSA(t3, s3, s1, s2, x6);
-    const uint32_t ones = s3 ^ x7, t4 = s3 & x7;
     KF_CSA(f1, tw1, t1, t2, t3);
-    const uint32_t twos = tw1 ^ t4; f2 = tw1 & t4; (void)tw2;
-    const uint32_t fours = f1 ^ f2, eights = f1 & f2;
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+    return __popc(s3) + __popc(x7) + 2 * __popc(tw1) + 4 * __popc(f1);
 }
 
 // ---- 1. gather the stereo-matched left descriptors of each pair into the keyframe store ----------------------
