@@ -412,7 +412,7 @@ def main():
     try:    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture, scaled to this batch size
         if args.config != "b":
             raise KeyError("traffic was captured for the headline config only")
-        with open(os.path.join(ROOT, "profiles", "r01h_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01k_traffic.json")) as f:
             tj = json.load(f)
         traffic = tj["traffic_bytes_per_launch"][dom] * B / tj["pairs_per_launch"] / max(stages[dom]["launches"], 1)
     except Exception:
