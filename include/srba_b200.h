@@ -196,6 +196,9 @@ int sfe_ipc_close(sfe_context* ctx, void* dptr);
 /* ---- timing helpers (CUDA events on sfe_stream()) -------------------------------------------- */
 int sfe_timer_start(sfe_context* ctx);
 int sfe_timer_stop(sfe_context* ctx, float* ms);       /* synchronises on the stop event        */
+/* Makes ctx's stream wait (on the device) for everything submitted so far on other's stream: joins two contexts that
+ * are used round-robin, e.g. before sfe_timer_stop so that one event pair spans the work of both. */
+int sfe_stream_wait(sfe_context* ctx, sfe_context* other);
 /* Per-kernel stage times of the most recent sfe_process_batch_* call made with profiling on.
  * Stage order: see sfe_stage_name(). */
 int sfe_set_profiling(sfe_context* ctx, int on);

@@ -324,6 +324,7 @@ extern "C" void sfe_destroy(sfe_context* c)
     cudaFreeHost(c->h_images); cudaFreeHost(c->h_kp); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_matches);
     cudaFreeHost(c->h_kp_count); cudaFreeHost(c->h_match_count); cudaFreeHost(c->h_status); cudaFreeHost(c->h_counts);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
     for (int i = 0; i <= ST_COUNT; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -755,6 +756,16 @@ extern "C" int sfe_ipc_close(sfe_context* c, void* dptr) { if (!c) return SFE_ER
 
 // ---- timing ---------------------------------------------------------------------------------------------
 extern "C" int sfe_timer_start(sfe_context* c) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaEventRecord(c->ev_start, c->stream)); return SFE_OK; }
+extern "C" int sfe_stream_wait(sfe_context* c, sfe_context* other)
+{
+    if (!c || !other) return SFE_ERR_INVALID;
+    if (c == other) return SFE_OK;
+    if (c->cfg.device != other->cfg.device) { c->err = "sfe_stream_wait: contexts live on different devices"; return SFE_ERR_INVALID; }
+    if (!other->ev_join) SFE_CUDA(c, cudaEventCreateWithFlags(&other->ev_join, cudaEventDisableTiming));
+    SFE_CUDA(c, cudaEventRecord(other->ev_join, other->stream));
+    SFE_CUDA(c, cudaStreamWaitEvent(c->stream, other->ev_join, 0));
+    return SFE_OK;
+}
 extern "C" int sfe_timer_stop(sfe_context* c, float* ms)
 {
     if (!c || !ms) return SFE_ERR_INVALID;

@@ -143,7 +143,7 @@ struct sfe_context {
     // graph cache, one per batch size
     std::vector<cudaGraphExec_t> graphs;
     // timing
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_join = nullptr;
     bool profiling = false;
     cudaEvent_t ev_stage[ST_COUNT + 1] = {};
     int graph_kernels = 0;                   // kernels per graph replay

@@ -80,6 +80,7 @@ def load_library():
     L.sfe_match_bf.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.sfe_match_bf_batch_device.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     L.sfe_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.sfe_stream_wait.argtypes = [vp, vp]
     L.sfe_set_profiling.argtypes = [vp, i32]
     L.sfe_stage_name.argtypes = [i32]; L.sfe_stage_name.restype = C.c_char_p
     L.sfe_stage_times.argtypes = [vp, vp, vp]
@@ -253,6 +254,7 @@ class StereoFrontEnd:
 
     # --- timing ---
     def timer_start(self): self._chk(self.lib.sfe_timer_start(self.h))
+    def stream_wait(self, other): self._chk(self.lib.sfe_stream_wait(self.h, other.h))
     def timer_stop(self):
         ms = C.c_float()
         self._chk(self.lib.sfe_timer_stop(self.h, C.byref(ms)))
