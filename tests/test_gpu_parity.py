@@ -377,3 +377,24 @@ def test_strided_and_ragged_batches(mods, scene_frames):
             assert np.array_equal(a, b)
     finally:
         fe.close()
+
+
+def test_two_contexts_joined_streams(mods, scene_frames):
+    """sfe_stream_wait: two contexts used round-robin, joined on the device, give the results of one context."""
+    frontend, _ = mods
+    frames = scene_frames(2)
+    a = frontend.StereoFrontEnd(max_pairs=2); b = frontend.StereoFrontEnd(max_pairs=2)
+    try:
+        a.upload(frames); b.upload(frames[::-1].copy())
+        a.timer_start()
+        for i in range(4):
+            (a, b)[i % 2].process_device(2)
+        a.stream_wait(b)
+        assert a.timer_stop() > 0.0
+        b.synchronize()
+        ka = a.get_values(0); kb = b.get_values(1)              # pair 0 of a == pair 1 of b (b holds the batch reversed)
+        for x, y in zip(ka, kb):
+            assert np.array_equal(x, y)
+        a.stream_wait(a)                                        # joining a context with itself is a no-op
+    finally:
+        a.close(); b.close()
