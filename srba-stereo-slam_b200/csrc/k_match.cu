@@ -180,7 +180,7 @@ void launch_match_rowband(sfe_context* c, int npairs)
     a.max_y_diff = c->cfg.max_y_diff; a.min_disp = c->cfg.min_disparity; a.max_disp = c->cfg.max_disparity;
     a.max_dist = c->orb_th; a.robust = c->cfg.robust_1to1;
     // enough CTAs to fill the GPU (2 waves of 148 SMs) however small the batch, at least 64 left keypoints per slice
-    a.slices = std::max(1, std::min({ (296 + npairs - 1) / npairs, (c->cfg.nfeatures + 63) / 64, 32 }));
+    a.slices = std::max(1, std::min({ (888 + npairs - 1) / npairs, (c->cfg.nfeatures + 63) / 64, 32 }));
     if (a.robust) cudaMemsetAsync(c->d_rb_owner, 0xff, sizeof(uint32_t) * (size_t)npairs * a.kp_cap, c->stream);
     rowband_match_kernel<<<dim3(a.slices, npairs), RB_THREADS, rowband_smem(c), c->stream>>>(a);
     rowband_compact_kernel<<<npairs, RB_THREADS, 0, c->stream>>>(a);
