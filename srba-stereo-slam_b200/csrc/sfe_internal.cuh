@@ -30,7 +30,7 @@
 #define BLUR_BOX_H 40       // shares the 160x40 maps with FAST (rows 38,39 unused)
 #define BLUR_ROWS (BLUR_TH + 6)
 
-#define SEL_THREADS 512
+#define SEL_THREADS 256
 #define SEL_TIE_SLACK 64   // extra slots per level for Harris-response ties
 
 struct LevelGeom {
