@@ -398,3 +398,42 @@ def test_two_contexts_joined_streams(mods, scene_frames):
         a.stream_wait(a)                                        # joining a context with itself is a no-op
     finally:
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("w,h,nlevels,scale,nfeat,fth,eth,bm,pm", [
+    (401, 303, 1, 1.2, 150, 7, 31, 0, 0),         # single level, low FAST threshold (many quick-test survivors)
+    (517, 389, 6, 1.1, 700, 35, 31, 0, 0),        # smaller scale step: wider source footprints in the pyramid kernel
+    (640, 480, 8, 1.25, 1200, 20, 19, 1, 1),      # largest scale step, smallest edge threshold, cv4 arithmetic
+    (333, 777, 5, 1.2, 400, 60, 40, 1, 0),        # portrait image, high threshold, mixed modes
+    (1023, 257, 2, 1.15, 3000, 12, 25, 0, 1),     # wide noisy strip: more keypoints per level than the shared-memory sort holds
+    (160, 120, 3, 1.2, 50, 127, 31, 0, 0),        # highest legal FAST threshold: (almost) nothing detected
+])
+def test_parameter_sweep(mods, w, h, nlevels, scale, nfeat, fth, eth, bm, pm):
+    """Configurations off the beaten path of the benchmark: every keypoint field and descriptor bit vs the oracle."""
+    frontend, orc = mods
+    rng = np.random.default_rng(w * 7 + h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = (96 + 60 * np.sin(xx / 9.0) * np.cos(yy / 7.0)).astype(np.float32)
+    for _ in range(60):                                                        # rectangles of random grey: real corners
+        x0, y0 = int(rng.integers(0, w - 8)), int(rng.integers(0, h - 8))
+        ww, hh = int(rng.integers(4, 60)), int(rng.integers(4, 60))
+        img[y0:y0 + hh, x0:x0 + ww] = rng.integers(0, 256)
+    img = np.clip(img + rng.normal(0, 30 if nfeat >= 2500 else 3, (h, w)), 0, 255).astype(np.uint8)
+    right = np.roll(img, -5, axis=1).copy()
+    fe = frontend.StereoFrontEnd(width=w, height=h, nlevels=nlevels, nfeatures=nfeat, scale_factor=scale, fast_threshold=fth,
+                                 edge_threshold=eth, blur_mode=bm, pyramid_mode=pm, max_pairs=1)
+    try:
+        fe.process_stereo(img, right)
+        kl, kr, dl, dr, m = fe.get_values(0)
+        sides = []
+        for im, gk, gd in ((img, kl, dl), (right, kr, dr)):
+            ok, od, _ = orc.orb_extract(im, nfeatures=nfeat, nlevels=nlevels, fast_threshold=fth, edge_threshold=eth, scale=scale,
+                                        blur_mode=bm, pyramid_mode=pm)
+            _assert_keypoints_equal(gk, ok)
+            assert np.array_equal(gd, od)
+            sides.append((ok, od))
+        om = orc.match_rowband(sides[0][0], sides[0][1], sides[1][0], sides[1][1], max_y_diff=2.0, max_dist=60)
+        for f in ("queryIdx", "trainIdx", "distance"):
+            assert np.array_equal(m[f], om[f]), f
+    finally:
+        fe.close()
