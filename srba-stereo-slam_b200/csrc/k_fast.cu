@@ -118,7 +118,8 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
             const int nrows = min(max(rlim - 4 * warp + 1, 0), 4);      // rows 4w .. 4w+nrows-1 lie inside the ROI (+1)
             cm = colok ? (cm & ((1u << (4 * nrows)) - 1u)) : 0u;
         }
-        if (ok4) cm |= quick(tw + (r4 + 3) * FAST_TP + j4) << 16;
+        // halo words: NMS only reads the pixel column next to the tile (byte 3 of word 0, byte 0 of word 33)
+        if (ok4) cm |= (quick(tw + (r4 + 3) * FAST_TP + j4) & (tid < 64 ? 0xfu : (j4 == 0 ? 0x8u : 0x1u))) << 16;
         // compaction: one shared atomic per thread that has survivors (ptxas aggregates same-address atomics across the
         // warp), then a short bit loop.  (A row-major warp-scan compaction was measured: fewer bank conflicts in phase B,
         // 1.68 vs 1.78 wavefronts per ring load, but 46 more instructions per warp - no gain.)
