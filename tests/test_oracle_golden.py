@@ -123,6 +123,25 @@ def test_blur_modes_properties():
         assert np.array_equal(orc.gauss7_blur(img[::-1], mode)[::-1], a)
 
 
+def test_blur_fixed_point_matches_independent_numpy_restatement():
+    """OpenCV 2.4 8-bit GaussianBlur(7x7, sigma 2): taps = cvRound(256 * getGaussianKernel), int32 row sums,
+    (column sum + 2^15) >> 16, saturate, BORDER_REFLECT_101 - restated here in numpy from the formulas, taps derived
+    from the Gaussian (not copied from the C file), and compared with the C oracle incl. saturated regions."""
+    x = np.arange(7) - 3
+    g = np.exp(-(x * x) / (2.0 * 2.0 * 2.0)); g /= g.sum()
+    taps = np.rint(g * 256).astype(np.int64)
+    assert taps.tolist() == [18, 34, 49, 55, 49, 34, 18]
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (57, 83), dtype=np.uint8)
+    img[10:30, 20:60] = 255; img[40:, :12] = 254; img[:6, 70:] = 0
+    p = np.pad(img.astype(np.int64), 3, mode="reflect")                       # numpy 'reflect' == BORDER_REFLECT_101
+    rows = sum(taps[k] * p[:, k:k + img.shape[1]] for k in range(7))
+    cols = sum(taps[k] * rows[k:k + img.shape[0], :] for k in range(7))
+    ref = np.minimum((cols + (1 << 15)) >> 16, 255).astype(np.uint8)
+    assert ref.max() == 255 and (cols.max() + (1 << 15)) >> 16 > 255          # the saturation branch is exercised
+    assert np.array_equal(orc.gauss7_blur(img, 0), ref)
+
+
 def test_rowband_conventions():
     rng = np.random.default_rng(1)
     n = 40
