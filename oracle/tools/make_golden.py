@@ -74,6 +74,19 @@ def main():
         d["kp_%d" % i] = kp_array(kp); d["desc_%d" % i] = desc
     np.savez_compressed(os.path.join(OUT, "orb_multilevel.npz"), n=3, **d)
 
+    # 4c. cv2.ORB end to end off the default parameters: scale factors 1.05 .. 1.25, edge thresholds 19 .. 45, other
+    #     FAST thresholds and level counts (cv4 arithmetic) - pins level sizes, quotas and coordinate scaling in general
+    d = {}
+    mid = synth.CorridorScene(seed=3, width=640, height=400).frame(2)[0]
+    d["img"] = mid
+    combos = ((400, 6, 1.1, 31, 20), (500, 8, 1.25, 31, 15), (300, 5, 1.2, 19, 20), (300, 4, 1.15, 45, 30), (800, 8, 1.05, 31, 20))
+    for i, (nf, nl, sf, et, th) in enumerate(combos):
+        orb = cv2.ORB_create(nfeatures=nf, nlevels=nl, scaleFactor=sf, edgeThreshold=et, fastThreshold=th)
+        kp, desc = orb.detectAndCompute(mid, None)
+        d["prm_%d" % i] = np.array([nf, nl, sf, et, th], np.float64)
+        d["kp_%d" % i] = kp_array(kp); d["desc_%d" % i] = desc
+    np.savez_compressed(os.path.join(OUT, "orb_params.npz"), n=len(combos), **d)
+
     # 5. BFMatcher(NORM_HAMMING): random descriptors with planted near-duplicates and exact ties
     Q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
     T = rng.integers(0, 256, (257, 32), dtype=np.uint8)

@@ -129,6 +129,34 @@ def test_golden_cv2_orb_multilevel(mods, golden):
         assert np.array_equal(dl, rdesc) and np.array_equal(dr, rdesc)
 
 
+def test_golden_cv2_orb_parameter_variants(mods, golden):
+    """The CUDA path against cv2.ORB outputs with scale factors 1.05 .. 1.25, edge thresholds 19 .. 45, 4 .. 8 levels
+    (cv4 arithmetic): every keypoint field and descriptor bit, straight against the committed cv2 vectors."""
+    frontend, orc = mods
+    g = golden("orb_params.npz")
+    img = g["img"]
+    h, w = img.shape
+    for i in range(int(g["n"])):
+        nf, nl, sf, et, th = g["prm_%d" % i]
+        if not 1.05 <= sf <= 1.25:
+            continue
+        fe = frontend.StereoFrontEnd(width=w, height=h, nlevels=int(nl), nfeatures=int(nf), scale_factor=float(sf), edge_threshold=int(et),
+                                     fast_threshold=int(th), blur_mode=1, pyramid_mode=1, max_pairs=1)
+        try:
+            fe.process_stereo(img, img)
+            kl, kr, dl, dr, m = fe.get_values(0)
+        finally:
+            fe.close()
+        ref, rdesc = g["kp_%d" % i], g["desc_%d" % i]
+        sc = np.array([orc.level_scale(int(o), float(sf)) for o in ref[:, 5]])
+        o = np.lexsort((np.rint(ref[:, 0] / sc), np.rint(ref[:, 1] / sc), ref[:, 5]))
+        ref, rdesc = ref[o], rdesc[o]
+        assert len(kl) == len(ref) == int(nf)
+        for j, f in enumerate(("x", "y", "size", "angle", "response", "octave", "class_id")):
+            assert np.array_equal(kl[f], ref[:, j].astype(kl[f].dtype)), (i, f)
+        assert np.array_equal(dl, rdesc) and np.array_equal(dr, rdesc)
+
+
 def test_runtime_thresholds_and_repeat(mods, scene_frames):
     """setFASTThreshold / setORBThreshold + request.repeat (EST.cpp:263-315)."""
     frontend, orc = mods

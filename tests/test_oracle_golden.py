@@ -66,8 +66,8 @@ def test_orb_single_level_matches_cv2(golden):
         assert np.array_equal(desc, rdesc)
 
 
-def _canonical(ref, rdesc, orc):
-    sc = np.array([orc.level_scale(int(o)) for o in ref[:, 5]])
+def _canonical(ref, rdesc, orc, scale=1.2):
+    sc = np.array([orc.level_scale(int(o), scale) for o in ref[:, 5]])
     o = np.lexsort((np.rint(ref[:, 0] / sc), np.rint(ref[:, 1] / sc), ref[:, 5]))
     return ref[o], rdesc[o]
 
@@ -87,6 +87,23 @@ def test_orb_multilevel_matches_cv2_end_to_end(golden):
             assert np.array_equal(kps[f], ref[:, j].astype(kps[f].dtype)), (i, f)
         assert np.array_equal(desc, rdesc)
         assert len(np.unique(kps["octave"])) == nl or i == 0
+
+
+def test_orb_parameter_variants_match_cv2(golden):
+    """cv2.ORB 4.13 with scale factors 1.05 .. 1.25, edge thresholds 19 .. 45, 4 .. 8 levels and other FAST thresholds:
+    every keypoint field and descriptor bit (cv4 arithmetic), so level sizes, quotas and coordinate scaling are pinned
+    beyond the default 1.2 / 31."""
+    g = golden("orb_params.npz")
+    img = g["img"]
+    for i in range(int(g["n"])):
+        nf, nl, sf, et, th = g["prm_%d" % i]
+        kps, desc, _ = orc.orb_extract(img, nfeatures=int(nf), nlevels=int(nl), fast_threshold=int(th), edge_threshold=int(et),
+                                       scale=float(sf), blur_mode=1, pyramid_mode=1)
+        ref, rdesc = _canonical(g["kp_%d" % i], g["desc_%d" % i], orc, float(sf))
+        assert len(kps) == len(ref) == int(nf)
+        for j, f in enumerate(("x", "y", "size", "angle", "response", "octave", "class_id")):
+            assert np.array_equal(kps[f], ref[:, j].astype(kps[f].dtype)), (i, f)
+        assert np.array_equal(desc, rdesc)
 
 
 def test_resize_exact_vs_reference_mode_differ_only_slightly():
