@@ -166,6 +166,7 @@ bow_topk_kernel(const double* __restrict__ score, int32_t* __restrict__ common, 
 extern "C" int sfe_bow_create(sfe_context* ctx, int nnodes, int nwords, const int32_t* child_ofs, const int32_t* child_idx,
                               const uint8_t* node_desc, const double* node_weight, const int32_t* node_word, sfe_bow** out)
 {
+    SFE_BIND_DEVICE(ctx);
     if (!ctx || !out || nnodes < 2 || nwords < 1 || nwords > 32768 || !child_ofs || !child_idx || !node_desc || !node_weight || !node_word)
         return SFE_ERR_INVALID;
     sfe_bow* b = new sfe_bow(); b->ctx = ctx; b->nnodes = nnodes; b->nwords = nwords;
@@ -213,6 +214,7 @@ extern "C" int sfe_bow_create(sfe_context* ctx, int nnodes, int nwords, const in
 
 extern "C" void sfe_bow_destroy(sfe_bow* b)
 {
+    SFE_BIND_DEVICE((b ? b->ctx : nullptr));
     if (!b) return;
     cudaFree(b->d_first); cudaFree(b->d_nchild); cudaFree(b->d_desc); cudaFree(b->d_word); cudaFree(b->d_weight);
     cudaFree(b->d_in); cudaFree(b->d_w); cudaFree(b->d_wt); cudaFree(b->d_vw); cudaFree(b->d_vv); cudaFree(b->d_vn);
@@ -237,6 +239,7 @@ static int bow_reserve(sfe_bow* b, int n)
 
 extern "C" int sfe_bow_transform_device(sfe_bow* b, const uint8_t* d_desc, int n, int32_t* d_word, double* d_weight)
 {
+    SFE_BIND_DEVICE((b ? b->ctx : nullptr));
     if (!b || n < 0) return SFE_ERR_INVALID;
     if (n == 0) return SFE_OK;
     const int threads = 256, blocks = (n * 8 + threads - 1) / threads;
@@ -266,6 +269,7 @@ static int bow_run(sfe_bow* b, const uint8_t* desc, int n, bool want_vector)
 
 extern "C" int sfe_bow_transform(sfe_bow* b, const uint8_t* desc, int n, int32_t* word, double* weight)
 {
+    SFE_BIND_DEVICE((b ? b->ctx : nullptr));
     if (!b || n < 0 || (n > 0 && (!desc || !word || !weight))) return SFE_ERR_INVALID;
     if (n == 0) return SFE_OK;
     int r = bow_run(b, desc, n, false); if (r) return r;
@@ -277,6 +281,7 @@ extern "C" int sfe_bow_transform(sfe_bow* b, const uint8_t* desc, int n, int32_t
 
 extern "C" int sfe_bow_vector(sfe_bow* b, const uint8_t* desc, int n, int32_t* out_word, double* out_val, int32_t* n_out)
 {
+    SFE_BIND_DEVICE((b ? b->ctx : nullptr));
     if (!b || n < 0 || !n_out) return SFE_ERR_INVALID;
     *n_out = 0;
     if (n == 0) return SFE_OK;
@@ -295,6 +300,7 @@ extern "C" int sfe_bow_db_size(const sfe_bow* b) { return b ? (int)b->entry_ofs.
 
 extern "C" int sfe_bow_db_add(sfe_bow* b, const uint8_t* desc, int n, int32_t* entry_id)
 {
+    SFE_BIND_DEVICE((b ? b->ctx : nullptr));
     if (!b || n < 0 || (n > 0 && !desc)) return SFE_ERR_INVALID;
     int32_t m = 0;
     cudaStream_t s = b->ctx->stream;
@@ -341,6 +347,7 @@ extern "C" int sfe_bow_db_add(sfe_bow* b, const uint8_t* desc, int n, int32_t* e
 
 extern "C" int sfe_bow_db_query(sfe_bow* b, const uint8_t* desc, int n, int max_results, int32_t* ids, double* scores, int32_t* n_out)
 {
+    SFE_BIND_DEVICE((b ? b->ctx : nullptr));
     if (!b || n < 0 || !n_out || max_results < 1 || max_results > 64 || !ids || !scores) return SFE_ERR_INVALID;
     *n_out = 0;
     const int ne = (int)b->entry_ofs.size() - 1;

@@ -348,6 +348,7 @@ kf_bf_kernel(const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs
 // ---- host side -------------------------------------------------------------------------------------------------------
 extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_frames, sfe_kfdb** out)
 {
+    SFE_BIND_DEVICE(ctx);
     if (!ctx || !bow || !out || capacity_frames < 1 || capacity_frames > (1 << 20)) return SFE_ERR_INVALID;
     sfe_kfdb* d = new sfe_kfdb(); d->ctx = ctx; d->bow = bow;
     d->cap_frames = capacity_frames; d->stride = ctx->pack.kp_cap; d->B = ctx->cfg.max_pairs;
@@ -380,6 +381,7 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
 
 extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
 {
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
     if (!d) return;
     cudaFree(d->d_msub); cudaFree(d->d_msub_n); cudaFree(d->d_dbw); cudaFree(d->d_dbv); cudaFree(d->d_dbn);
     cudaFree(d->d_word); cudaFree(d->d_weight); cudaFree(d->d_tmask); cudaFree(d->d_dense); cudaFree(d->d_score);
@@ -398,6 +400,7 @@ extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* src, int npai
 
 extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
 {
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
     return d ? sfe_kfdb_process_batch_on(d, d->ctx, npairs) : SFE_ERR_INVALID;
 }
 
@@ -405,6 +408,7 @@ extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
 // batches from different contexts are serialised on the database through an event.
 extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs)
 {
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
     if (!d || !c || npairs < 1 || npairs > d->B) return SFE_ERR_INVALID;
     if (c->pack.kp_cap != d->stride || c->cfg.device != d->ctx->cfg.device) { c->err = "source context does not match the keyframe database"; return SFE_ERR_INVALID; }
     sfe_bow* b = d->bow;
@@ -449,6 +453,7 @@ extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs
 extern "C" int sfe_kfdb_results(sfe_kfdb* d, const int32_t** query_ids, const double** query_scores, const int32_t** query_n,
                                 const int32_t** pair_kf, const uint32_t** best, const int32_t** matched_n)
 {
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
     if (!d) return SFE_ERR_INVALID;
     cudaStream_t s = d->last_stream ? d->last_stream : d->ctx->stream; const int n = d->last_n; const size_t cap = d->stride;
     if (n == 0) { d->ctx->err = "no batch processed"; return SFE_ERR_STATE; }

@@ -167,7 +167,9 @@ static size_t rowband_smem(const sfe_context* c)
 
 void prepare_rowband(sfe_context* c)
 {
-    cudaFuncSetAttribute(rowband_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowband_smem(c));
+    // the attribute belongs to the kernel function (per device), not to the context: never lower it, or a second,
+    // smaller context would break the launches of an earlier, larger one
+    sfe_raise_dynamic_smem((const void*)rowband_match_kernel, c->cfg.device, (int)rowband_smem(c));
 }
 
 void launch_match_rowband(sfe_context* c, int npairs)
@@ -250,6 +252,17 @@ void launch_bf_init(cudaStream_t s, uint32_t* best, int n)
 {
     if (n <= 0) return;
     bf_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(best, n);
+}
+
+// Same, for the batched entry point whose total query count q_ofs[npairs] only exists on the device.
+__global__ void bf_init_ofs_kernel(uint32_t* best, const int32_t* __restrict__ q_ofs, int npairs)
+{
+    const int n = q_ofs[npairs];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) best[i] = 0xffffffffu;
+}
+void launch_bf_init_ofs(cudaStream_t s, uint32_t* best, const int32_t* d_q_ofs, int npairs)
+{
+    bf_init_ofs_kernel<<<148 * 4, 256, 0, s>>>(best, d_q_ofs, npairs);
 }
 
 

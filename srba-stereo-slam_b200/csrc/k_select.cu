@@ -85,14 +85,44 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
             kth_from_top(hist, 2 * q, lane, thr, above);
             if (q == 0) thr = 256;
         }
-        if (lane == 0) s_thr = thr;
+        if (lane == 0) { s_thr = thr; s_k = (n > 2 * q && thr < 256 && above + hist[thr] > cand_cap) ? cand_cap - above : -1; }
     }
     __syncthreads();
     const int thr = s_thr;
+    // Ties at the cut that do not fit the shared candidate list (binary / saturated images: most corners score the
+    // same): OpenCV would carry every tie into the Harris stage; here the ties are cut DETERMINISTICALLY to the ones
+    // with the smallest (y, x) -- a 3-pass radix select on the inverted 24-bit position key -- instead of failing the
+    // frame with an order-dependent truncation.
+    uint32_t tie_max = 0x00ffffffu;
+    if (s_k >= 0) {
+        if (tid == 0) s_prefix = 0u;
+        uint32_t mask = 0u;
+        for (int shift = 16; shift >= 0; shift -= 8) {
+            __syncthreads();
+            for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int i = tid; i < n; i += SEL_THREADS) {
+                const uint32_t r = rl[i];
+                const uint32_t k = 0x00ffffffu - (r & 0x00ffffffu);
+                if ((int)(r >> 24) == thr && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int b, above;
+                kth_from_top(hist, s_k, lane, b, above);
+                __syncwarp();
+                if (lane == 0) { s_k = s_k - above; s_prefix = prefix | ((uint32_t)b << shift); }
+            }
+            mask |= 255u << shift;
+        }
+        __syncthreads();
+        tie_max = 0x00ffffffu - s_prefix;
+    }
     for (int base = 0; base < n; base += SEL_THREADS) {          // warp-aggregated compaction
         const int i = base + tid;
         uint32_t r = 0; bool keepc = false;
-        if (i < n) { r = rl[i]; keepc = (int)(r >> 24) >= thr; }
+        if (i < n) { r = rl[i]; const int sc = (int)(r >> 24); keepc = sc > thr || (sc == thr && (r & 0x00ffffffu) <= tie_max); }
         const uint32_t bal = __ballot_sync(0xffffffffu, keepc);
         if (bal) {
             int wb = 0;
@@ -232,7 +262,7 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
 
 void prepare_select(sfe_context* c)
 {
-    cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sel_cand_cap * 8);
+    sfe_raise_dynamic_smem((const void*)select_kernel, c->cfg.device, c->sel_cand_cap * 8);   // per function, never lowered
 }
 
 void launch_select(sfe_context* c, int nimg)

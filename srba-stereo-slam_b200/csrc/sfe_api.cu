@@ -11,10 +11,21 @@
 
 void sfe_upload_blur_taps(const float* taps);
 void launch_bf_init(cudaStream_t s, uint32_t* best, int n);
+void launch_bf_init_ofs(cudaStream_t s, uint32_t* best, const int32_t* d_q_ofs, int npairs);
 void launch_bf_pairs(cudaStream_t s, const uint8_t* dq, const uint8_t* const* train_bases, const sfe_bf_pair* pairs,
                      int npairs, int max_nq, uint32_t* best);
 
 static std::string g_create_err;
+
+#include <map>
+#include <mutex>
+void sfe_raise_dynamic_smem(const void* func, int device, int bytes)
+{
+    static std::mutex mu; static std::map<std::pair<const void*, int>, int> cur;
+    std::lock_guard<std::mutex> lk(mu);
+    int& have = cur[std::make_pair(func, device)];
+    if (bytes > have) { cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); have = bytes; }
+}
 
 static inline int cv_round_d(double v) { return (int)lrint(v); }
 static inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
@@ -303,6 +314,7 @@ static int create_impl(sfe_context* c)
 extern "C" int sfe_create(const sfe_config* cfg, sfe_context** out)
 {
     if (!cfg || !out) { g_create_err = "null argument"; return SFE_ERR_INVALID; }
+    SfeDeviceGuard guard(cfg->device);     // create_impl binds the device; the caller's current device is restored on return
     sfe_context* c = new sfe_context();
     c->cfg = *cfg;
     const int r = create_impl(c);
@@ -313,6 +325,7 @@ extern "C" int sfe_create(const sfe_config* cfg, sfe_context** out)
 
 extern "C" void sfe_destroy(sfe_context* c)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
@@ -441,6 +454,7 @@ extern "C" uint8_t* sfe_host_staging(sfe_context* c, size_t* bytes)
 
 extern "C" int sfe_upload_batch(sfe_context* c, const uint8_t* images, int npairs, size_t stride, size_t image_stride)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     stage_mark(c, ST_H2D);
     return upload(c, images, npairs, stride, image_stride);
@@ -448,6 +462,7 @@ extern "C" int sfe_upload_batch(sfe_context* c, const uint8_t* images, int npair
 
 extern "C" int sfe_process_batch_device(sfe_context* c, int npairs)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     return run_batch(c, npairs);
 }
@@ -464,6 +479,7 @@ static int fold_status(sfe_context* c, int npairs)
 
 extern "C" int sfe_synchronize(sfe_context* c)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     if (c->have_results) return fold_status(c, c->last_npairs);
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -472,6 +488,7 @@ extern "C" int sfe_synchronize(sfe_context* c)
 
 extern "C" int sfe_process_batch_host(sfe_context* c, const uint8_t* images, int npairs, size_t stride, size_t image_stride)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     stage_mark(c, ST_H2D);
     int r = upload(c, images, npairs, stride, image_stride);
@@ -483,6 +500,7 @@ extern "C" int sfe_process_batch_host(sfe_context* c, const uint8_t* images, int
 
 extern "C" int sfe_process_stereo(sfe_context* c, const uint8_t* left, const uint8_t* right, size_t stride, int repeat)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     if (!repeat) {
         if (!left || !right) { c->err = "null image"; return SFE_ERR_INVALID; }
@@ -526,6 +544,7 @@ static int fetch_counts(sfe_context* c)
 
 extern "C" int sfe_get_counts(sfe_context* c, int pair, sfe_pair_counts* out)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !out) return SFE_ERR_INVALID;
     int r = fetch_counts(c); if (r) return r;
     if (pair < 0 || pair >= c->last_npairs) { c->err = "pair out of range"; return SFE_ERR_INVALID; }
@@ -536,6 +555,7 @@ extern "C" int sfe_get_counts(sfe_context* c, int pair, sfe_pair_counts* out)
 extern "C" int sfe_get_values(sfe_context* c, int pair, sfe_keypoint* kl, sfe_keypoint* kr, uint8_t* dl, uint8_t* dr,
                               sfe_dmatch* m, sfe_pair_counts* counts)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     int r = fetch_counts(c); if (r) return r;
     if (pair < 0 || pair >= c->last_npairs) { c->err = "pair out of range"; return SFE_ERR_INVALID; }
@@ -575,6 +595,7 @@ static void fill_counts(sfe_context* c)
 
 extern "C" int sfe_submit_batch_host(sfe_context* c, const uint8_t* images, int npairs, size_t stride, size_t image_stride)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     int r = upload(c, images, npairs, stride, image_stride);
     if (r) return r;
@@ -586,6 +607,7 @@ extern "C" int sfe_submit_batch_host(sfe_context* c, const uint8_t* images, int 
 extern "C" int sfe_wait_batch(sfe_context* c, const sfe_keypoint** kps, const uint8_t** desc, const sfe_dmatch** matches,
                               const sfe_pair_counts** counts)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     if (!c->have_results) { c->err = "no batch in flight"; return SFE_ERR_STATE; }
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -604,6 +626,7 @@ extern "C" int sfe_wait_batch(sfe_context* c, const sfe_keypoint** kps, const ui
 extern "C" int sfe_download_batch(sfe_context* c, const sfe_keypoint** kps, const uint8_t** desc, const sfe_dmatch** matches,
                                   const sfe_pair_counts** counts)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     if (!c->have_results) { c->err = "no results"; return SFE_ERR_STATE; }
     const int np = c->last_npairs; const size_t cap = c->pack.kp_cap;
@@ -620,6 +643,7 @@ extern "C" int sfe_download_batch(sfe_context* c, const sfe_keypoint** kps, cons
 
 extern "C" int sfe_get_level(sfe_context* c, int img, int level, int blurred, uint8_t* out)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !out || level < 0 || level >= c->pack.nlevels || img < 0 || img >= c->NI) return SFE_ERR_INVALID;
     const LevelGeom& g = c->pack.g[level];
     const uint8_t* base = (blurred ? c->d_blur : c->d_pyr) + g.lvl_ofs + (size_t)img * g.img_bytes;
@@ -630,6 +654,7 @@ extern "C" int sfe_get_level(sfe_context* c, int img, int level, int blurred, ui
 
 extern "C" int sfe_get_raw_corners(sfe_context* c, int img, int level, uint32_t* out, int cap, int32_t* count)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || level < 0 || level >= c->pack.nlevels || img < 0 || img >= c->NI || !count) return SFE_ERR_INVALID;
     const LevelGeom& g = c->pack.g[level];
     int32_t n = 0;
@@ -647,6 +672,7 @@ extern "C" int sfe_get_raw_corners(sfe_context* c, int img, int level, uint32_t*
 extern "C" int sfe_device_results(sfe_context* c, const void** kps, const void** desc, const void** counts, const void** matches,
                                   const void** match_counts)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     if (kps) *kps = c->d_kp; if (desc) *desc = c->d_desc; if (counts) *counts = c->d_kp_count;
     if (matches) *matches = c->d_matches; if (match_counts) *match_counts = c->d_match_count;
@@ -657,17 +683,23 @@ extern "C" int sfe_device_results(sfe_context* c, const void** kps, const void**
 extern "C" int sfe_match_bf_batch_device(sfe_context* c, const uint8_t* dq, const int32_t* dqo, const uint8_t* dt, const int32_t* dto,
                                          int npairs, int max_nq, uint32_t* d_best)
 {
-    if (!c || !dq || !dqo || !dt || !dto || !d_best || npairs < 1 || npairs > 65535) return SFE_ERR_INVALID;
+    SFE_BIND_DEVICE(c);
+    if (!c || !dq || !dqo || !dt || !dto || !d_best || npairs < 1 || npairs > 65535 || max_nq < 1) return SFE_ERR_INVALID;
+    // the kernel merges its train splits with atomicMin and returns early for empty train sets: the keys must start
+    // at 0xFFFFFFFF.  One init kernel walks the query offsets (they live on the device) up to q_ofs[npairs].
+    launch_bf_init_ofs(c->stream, d_best, dqo, npairs);
     launch_match_bf(c->stream, dq, dqo, dt, dto, npairs, max_nq, d_best);
-    c->launches++;
+    c->launches += 2;
     SFE_CUDA(c, cudaGetLastError());
     return SFE_OK;
 }
 
 extern "C" int sfe_match_bf(sfe_context* c, const uint8_t* q, int nq, const uint8_t* t, int nt, sfe_dmatch* out, int32_t* n_out)
 {
-    if (!c || nq < 0 || nt < 0 || nt > 65535 || !n_out) return SFE_ERR_INVALID;
+    SFE_BIND_DEVICE(c);
+    if (!c || nq < 0 || nt < 0 || !n_out) return SFE_ERR_INVALID;
     *n_out = 0;
+    if (nt > 65535) { c->err = "sfe_match_bf: train set larger than 65535 descriptors (the packed key keeps 16 index bits)"; return SFE_ERR_INVALID; }
     if (nq == 0 || nt == 0) return SFE_OK;        // BFMatcher: empty train set -> no matches
     if (!q || !t || !out) return SFE_ERR_INVALID;
     if (nq > c->bf_cap_q) {
@@ -703,6 +735,7 @@ extern "C" int sfe_match_bf(sfe_context* c, const uint8_t* q, int nq, const uint
 extern "C" int sfe_match_bf_pairs_device(sfe_context* c, const uint8_t* d_query, const uint8_t* const* d_train_bases,
                                          const sfe_bf_pair* d_pairs, int npairs, int max_nq, uint32_t* d_best, size_t best_entries)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !d_query || !d_train_bases || !d_pairs || !d_best || npairs < 1 || npairs > 65535 * 16) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaMemsetAsync(d_best, 0xff, best_entries * sizeof(uint32_t), c->stream));
     for (int p0 = 0; p0 < npairs; p0 += 65535) {                 // gridDim.z limit
@@ -717,13 +750,15 @@ extern "C" int sfe_match_bf_pairs_device(sfe_context* c, const uint8_t* d_query,
 // ---- raw device memory + CUDA IPC (peer-mapped keyframe stores across the one-process-per-GPU ranks) ------------
 extern "C" int sfe_device_alloc(sfe_context* c, size_t bytes, void** out)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !out) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaMalloc(out, bytes));
     return SFE_OK;
 }
-extern "C" int sfe_device_free(sfe_context* c, void* p) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaFree(p)); return SFE_OK; }
+extern "C" int sfe_device_free(sfe_context* c, void* p) { if (!c) return SFE_ERR_INVALID; SFE_BIND_DEVICE(c); SFE_CUDA(c, cudaFree(p)); return SFE_OK; }
 extern "C" int sfe_copy_h2d(sfe_context* c, void* dst, const void* src, size_t bytes)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -731,6 +766,7 @@ extern "C" int sfe_copy_h2d(sfe_context* c, void* dst, const void* src, size_t b
 }
 extern "C" int sfe_copy_d2h(sfe_context* c, void* dst, const void* src, size_t bytes)
 {
+    SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -738,6 +774,7 @@ extern "C" int sfe_copy_d2h(sfe_context* c, void* dst, const void* src, size_t b
 }
 extern "C" int sfe_ipc_export(sfe_context* c, const void* dptr, uint8_t handle[64])
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !dptr || !handle) return SFE_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
@@ -747,17 +784,19 @@ extern "C" int sfe_ipc_export(sfe_context* c, const void* dptr, uint8_t handle[6
 }
 extern "C" int sfe_ipc_import(sfe_context* c, const uint8_t handle[64], void** dptr)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !handle || !dptr) return SFE_ERR_INVALID;
     cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
     SFE_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
     return SFE_OK;
 }
-extern "C" int sfe_ipc_close(sfe_context* c, void* dptr) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaIpcCloseMemHandle(dptr)); return SFE_OK; }
+extern "C" int sfe_ipc_close(sfe_context* c, void* dptr) { if (!c) return SFE_ERR_INVALID; SFE_BIND_DEVICE(c); SFE_CUDA(c, cudaIpcCloseMemHandle(dptr)); return SFE_OK; }
 
 // ---- timing ---------------------------------------------------------------------------------------------
-extern "C" int sfe_timer_start(sfe_context* c) { if (!c) return SFE_ERR_INVALID; SFE_CUDA(c, cudaEventRecord(c->ev_start, c->stream)); return SFE_OK; }
+extern "C" int sfe_timer_start(sfe_context* c) { if (!c) return SFE_ERR_INVALID; SFE_BIND_DEVICE(c); SFE_CUDA(c, cudaEventRecord(c->ev_start, c->stream)); return SFE_OK; }
 extern "C" int sfe_stream_wait(sfe_context* c, sfe_context* other)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !other) return SFE_ERR_INVALID;
     if (c == other) return SFE_OK;
     if (c->cfg.device != other->cfg.device) { c->err = "sfe_stream_wait: contexts live on different devices"; return SFE_ERR_INVALID; }
@@ -768,6 +807,7 @@ extern "C" int sfe_stream_wait(sfe_context* c, sfe_context* other)
 }
 extern "C" int sfe_timer_stop(sfe_context* c, float* ms)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !ms) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     SFE_CUDA(c, cudaEventSynchronize(c->ev_stop));
@@ -783,6 +823,7 @@ extern "C" const char* sfe_stage_name(int s)
 }
 extern "C" int sfe_stage_times(sfe_context* c, float* ms, int32_t* launches)
 {
+    SFE_BIND_DEVICE(c);
     if (!c || !ms) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
     const int L = c->pack.nlevels;

@@ -153,6 +153,22 @@ struct sfe_context {
     int bf_cap_q = 0, bf_cap_t = 0;
 };
 
+// Binds the context's device for the duration of a public entry point (and restores the caller's): two contexts on
+// different GPUs in one process, or a worker thread whose current device is not the context's, must not launch on /
+// allocate from the wrong device.
+struct SfeDeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit SfeDeviceGuard(int dev)
+    {
+        if (dev < 0 || cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+        if (prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~SfeDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    SfeDeviceGuard(const SfeDeviceGuard&) = delete;
+    SfeDeviceGuard& operator=(const SfeDeviceGuard&) = delete;
+};
+#define SFE_BIND_DEVICE(c) SfeDeviceGuard sfe_dev_guard__((c) ? (c)->cfg.device : -1)
+
 #define SFE_CUDA(ctx, call)                                                                   \
     do {                                                                                      \
         cudaError_t e__ = (call);                                                             \
@@ -161,6 +177,9 @@ struct sfe_context {
             return SFE_ERR_CUDA;                                                              \
         }                                                                                     \
     } while (0)
+
+// Raises (never lowers) a kernel's dynamic shared memory limit on `device`; defined in sfe_api.cu.
+void sfe_raise_dynamic_smem(const void* func, int device, int bytes);
 
 // kernel launchers (defined in the per-stage .cu files)
 void launch_pyramid_level(sfe_context* c, int level, int nimg);

@@ -15,7 +15,10 @@ bool dumpKeypointsToStream(std::ostream& stream, const TKeyPointList& keypoints,
     }
     const int drows = descriptors.rows, dcols = descriptors.cols, dtype = descriptors.type();
     wr(stream, drows); wr(stream, dcols); wr(stream, dtype);
-    if (drows > 0 && dcols > 0) stream.write(reinterpret_cast<const char*>(descriptors.ptr(0)), (std::streamsize)drows * dcols);
+    // the reference walks the elements with MatIterator_<uchar> (EST.cpp:2474-2480): one byte per element, row by row,
+    // so a non-continuous Mat (row range / ROI view under real OpenCV) must not be written from ptr(0) in one piece
+    if (dtype != CV_8U) return false;
+    for (int r = 0; r < drows && dcols > 0; ++r) stream.write(reinterpret_cast<const char*>(descriptors.ptr(r)), (std::streamsize)dcols);
     return stream.good();
 }
 
@@ -33,8 +36,9 @@ bool loadKeypointsFromStream(std::istream& stream, TKeyPointList& keypoints, cv:
     int drows = 0, dcols = 0, dtype = 0;
     rd(stream, drows); rd(stream, dcols); rd(stream, dtype);
     if (!stream.good() || drows < 0 || dcols < 0 || (size_t)drows * dcols > (1u << 30)) return false;
+    if (dtype != CV_8U) return false;
     descriptors.create(drows, dcols, dtype);
-    if (drows > 0 && dcols > 0) stream.read(reinterpret_cast<char*>(descriptors.ptr(0)), (std::streamsize)drows * dcols);
+    for (int r = 0; r < drows && dcols > 0; ++r) stream.read(reinterpret_cast<char*>(descriptors.ptr(r)), (std::streamsize)dcols);
     return stream.good();
 }
 

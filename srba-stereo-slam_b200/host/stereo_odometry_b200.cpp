@@ -117,18 +117,25 @@ bool CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& req, 
     if (cnt.n_right) std::memcpy(m_descR.ptr(0), dr.data(), (size_t)cnt.n_right * 32);
 
     // ---- inter-frame matching (ifmDescBF) on the stereo-matched left descriptors: id propagation ----------------
+    // A new frame (repeat == false) first retires the last call's result to "previous frame"; request.repeat re-runs
+    // detection on the same images (EST.cpp:278,285,315), so it must be matched against that SAME previous frame
+    // again and may not keep the ids its discarded first attempt consumed.
+    if (!req.repeat) {
+        if (m_have_frame) { m_prev_matched_desc = m_cur_matched_desc; m_prev_ids = m_ids; }
+        m_next_id_at_frame_start = m_next_id;
+    } else {
+        m_next_id = m_next_id_at_frame_start;
+    }
     const int nm = cnt.n_matches;
     cv::Mat cur(nm, 32, CV_8U);
     for (int k = 0; k < nm; ++k) std::memcpy(cur.ptr(k), m_descL.ptr(m_matches[k].queryIdx), 32);
     std::vector<size_t> ids(nm);
     size_t tracked = 0, tracked_kf = 0;
     std::vector<sfe_dmatch> ifm(std::max(nm, 1)); int32_t nifm = 0;
-    const int npre = req.repeat ? 0 : m_prev_matched_desc.rows;      // a repeated frame re-matches against the same previous frame
     const cv::Mat& pre = m_prev_matched_desc;
     if (nm > 0 && pre.rows > 0) {
         if (sfe_match_bf(m_ctx, cur.ptr(0), nm, pre.ptr(0), pre.rows, ifm.data(), &nifm) != SFE_OK) { m_err = sfe_last_error(m_ctx); return false; }
     }
-    (void)npre;
     std::set<size_t> kfset(m_kf_ids.begin(), m_kf_ids.end());
     std::vector<char> claimed(m_prev_ids.size(), 0);
     for (int k = 0; k < nm; ++k) {
@@ -136,9 +143,7 @@ bool CStereoOdometryEstimator::processNewImagePair(TStereoOdometryRequest& req, 
         if (ok) { ids[k] = m_prev_ids[ifm[k].trainIdx]; claimed[ifm[k].trainIdx] = 1; ++tracked; if (kfset.count(ids[k])) ++tracked_kf; }
         else ids[k] = m_next_id++;
     }
-    m_ids = ids;
-    if (!req.repeat || !m_have_frame) { /* the current frame becomes "previous" for the next call */ }
-    m_prev_matched_desc = cur; m_prev_ids = ids; m_have_frame = true;
+    m_ids = ids; m_cur_matched_desc = cur; m_have_frame = true;
 
     res.detected_feats.assign(1, std::make_pair((size_t)cnt.n_left, (size_t)cnt.n_right));
     res.stereo_matches.assign(1, (size_t)cnt.n_matches);

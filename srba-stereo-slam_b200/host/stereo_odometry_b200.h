@@ -122,8 +122,10 @@ private:
     std::string m_err;
     // current frame (host copies of the GPU results)
     std::vector<cv::KeyPoint> m_kpL, m_kpR; cv::Mat m_descL, m_descR; std::vector<cv::DMatch> m_matches; std::vector<size_t> m_ids;
-    // previous frame, for ifmDescBF id propagation
-    cv::Mat m_prev_matched_desc; std::vector<size_t> m_prev_ids;
+    // previous frame (the last NON-repeat call's predecessor), for ifmDescBF id propagation; the current frame's
+    // matched descriptors are only retired to "previous" when the caller moves on to a new frame
+    cv::Mat m_prev_matched_desc, m_cur_matched_desc; std::vector<size_t> m_prev_ids;
+    size_t m_next_id_at_frame_start = 0;
     std::vector<size_t> m_kf_ids;                     // ids alive at the last keyframe / resetIds()
     size_t m_next_id = 0; bool m_have_frame = false;
 };

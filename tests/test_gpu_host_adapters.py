@@ -105,16 +105,22 @@ def test_adaptive_threshold_loop(tmp_path):
     data = open(ob, "rb").read(); off = 0
     fast_th, orb_th = 20, 60                          # adapter defaults: fast 5..30, orb 30..100 (example.ini:15-16,45-46)
     seen_repeat = False
+    MD = frontend.DMATCH_DTYPE
+    prev = None; next_id = 0
     for k in range(NF):
         calls, f_th, o_th = struct.unpack_from("3i", data, off); off += 12
         nl, nr, nm, tracked, nq, nda = struct.unpack_from("6i", data, off); off += 24
-        off += 28 * nl + 28 * nr + 32 * nl + 32 * nr + 16 * nm + 8 * nm + 12 * nq + 16 * nda
+        off += 28 * nl + 28 * nr + 32 * nl + 32 * nr
+        mm = np.frombuffer(data, MD, nm, off); off += 16 * nm
+        ids = np.frombuffer(data, np.int64, nm, off); off += 8 * nm
+        off += 12 * nq + 16 * nda
         # ---- replay
         ecalls = 0
         while True:
             ol, odl, _ = orc.orb_extract(frames[k, 0], nfeatures=NFEAT, nlevels=NL, fast_threshold=fast_th)
             orr, odr, _ = orc.orb_extract(frames[k, 1], nfeatures=NFEAT, nlevels=NL, fast_threshold=fast_th)
-            m = len(orc.match_rowband(ol, odl, orr, odr, max_dist=orb_th)); ecalls += 1
+            om = orc.match_rowband(ol, odl, orr, odr, max_dist=orb_th)
+            m = len(om); ecalls += 1
             repeat = False
             if m < MINM:
                 if fast_th > 5: fast_th = max(5, min(30, max(0, fast_th - 10))); repeat = True
@@ -130,4 +136,25 @@ def test_adaptive_threshold_loop(tmp_path):
                 break
         seen_repeat |= ecalls > 1
         assert (calls, f_th, o_th, nm) == (ecalls, fast_th, orb_th, m), k
+        assert np.array_equal(mm["queryIdx"], om["queryIdx"]) and np.array_equal(mm["trainIdx"], om["trainIdx"])
+        # id propagation across a REPEATED frame (EST.cpp:263-315, :359-378): only the last attempt counts, it is matched
+        # against the true previous frame (not against the frame's own discarded first attempt) and the ids the discarded
+        # attempts consumed are handed out again
+        cur = odl[om["queryIdx"]]
+        exp_ids = np.zeros(m, np.int64); exp_tracked = 0
+        if prev is None:
+            exp_ids = np.arange(m, dtype=np.int64); next_id = m
+        else:
+            bf = orc.match_bf(cur, prev[0]); claimed = set()
+            for i in range(m):
+                t = int(bf["trainIdx"][i]) if len(bf) else -1
+                if len(bf) and bf["distance"][i] <= 60 and t not in claimed:
+                    exp_ids[i] = prev[1][t]; claimed.add(t); exp_tracked += 1
+                else:
+                    exp_ids[i] = next_id; next_id += 1
+        assert np.array_equal(ids, exp_ids), (k, ecalls)
+        assert tracked == exp_tracked, (k, ecalls, tracked, exp_tracked)
+        if ecalls > 1 and prev is not None:
+            assert tracked < m            # a frame matched against its own first attempt would track (almost) everything
+        prev = (cur, exp_ids)
     assert off == len(data) and seen_repeat
