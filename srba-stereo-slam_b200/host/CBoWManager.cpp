@@ -74,38 +74,51 @@ void loadFlatVocabulary(const std::string& filename, TFlatVocabulary& v)
 
 CBoWManager::~CBoWManager() { if (m_bow) sfe_bow_destroy(m_bow); }
 
+void CBoWManager::loadVocabulary(const std::string& voc_filename)
+{
+    m_host_voc.reset(new TFlatVocabulary()); loadFlatVocabulary(voc_filename, *m_host_voc);
+    if (m_bow) { sfe_bow_destroy(m_bow); m_bow = nullptr; }
+}
+
+void CBoWManager::ensureUploaded()
+{
+    if (m_bow) return;
+    if (!m_host_voc) throw std::runtime_error("CBoWManager: no vocabulary loaded");
+    if (!m_ctx) m_ctx = rso::CStereoOdometryEstimator::currentContext();
+    if (!m_ctx) throw std::runtime_error("CBoWManager: no GPU context yet (process a stereo pair first or call setContext)");
+    const TFlatVocabulary& v = *m_host_voc;
+    if (sfe_bow_create(m_ctx, v.nnodes, v.nwords, v.child_ofs.data(), v.child_idx.data(), v.node_desc.data(), v.node_weight.data(),
+                       v.node_word.data(), &m_bow) != SFE_OK)
+        throw std::runtime_error(std::string("sfe_bow_create: ") + sfe_last_error(m_ctx));
+    m_host_voc.reset();
+}
+
 void CBoWManager::loadVocabulary(sfe_context* ctx, const std::string& voc_filename)
 {
-    TFlatVocabulary v; loadFlatVocabulary(voc_filename, v);
-    m_ctx = ctx;
-    if (m_bow) { sfe_bow_destroy(m_bow); m_bow = nullptr; }
-    if (sfe_bow_create(ctx, v.nnodes, v.nwords, v.child_ofs.data(), v.child_idx.data(), v.node_desc.data(), v.node_weight.data(),
-                       v.node_word.data(), &m_bow) != SFE_OK)
-        throw std::runtime_error(std::string("sfe_bow_create: ") + sfe_last_error(ctx));
+    m_ctx = ctx; loadVocabulary(voc_filename); ensureUploaded();
+}
+
+void CBoWManager::loadVocabularyFromConfigFile(const mrpt::utils::CConfigFile& config, const std::string& section, const std::string& param)
+{
+    std::string voc = config.read_string(section, param, "", true);
+    if (voc.empty()) throw std::runtime_error("vocabulary file name is empty in [" + section + "] " + param);
+    auto exists = [](const std::string& f) { std::ifstream t(f.c_str()); return t.good(); };
+    if (!exists(voc)) {                                                // relative to the ini file's directory
+        const std::string& ini = config.getAssociatedFile(); const size_t sl = ini.find_last_of('/');
+        if (sl != std::string::npos && exists(ini.substr(0, sl + 1) + voc)) voc = ini.substr(0, sl + 1) + voc;
+        else throw std::runtime_error("Assert file existence failed: " + voc);                   // ASSERT_FILE_EXISTS_, CBoWManager.h:63
+    }
+    loadVocabulary(voc);
 }
 
 void CBoWManager::loadVocabularyFromConfigFile(sfe_context* ctx, const std::string& ini_file, const std::string& section, const std::string& param)
 {
-    std::ifstream f(ini_file.c_str());
-    std::string line, sec, voc;
-    while (std::getline(f, line)) {
-        const size_t c = line.find("//"); if (c != std::string::npos) line = line.substr(0, c);
-        const size_t a = line.find_first_not_of(" \t");
-        if (a == std::string::npos) continue;
-        if (line[a] == '[') { sec = line.substr(a + 1, line.find(']') - a - 1); continue; }
-        const size_t eq = line.find('=');
-        if (eq == std::string::npos || sec != section) continue;
-        std::string key = line.substr(a, eq - a); key.erase(key.find_last_not_of(" \t") + 1);
-        if (key != param) continue;
-        voc = line.substr(eq + 1);
-        voc.erase(0, voc.find_first_not_of(" \t")); voc.erase(voc.find_last_not_of(" \t\r\n") + 1);
-    }
-    if (voc.empty()) throw std::runtime_error("vocabulary file name not found in [" + section + "] " + param);   // ASSERT_FILE_EXISTS_, CBoWManager.h:63
-    loadVocabulary(ctx, voc);
+    m_ctx = ctx; loadVocabularyFromConfigFile(mrpt::utils::CConfigFile(ini_file), section, param); ensureUploaded();
 }
 
 void CBoWManager::insertIntoDB(const CStereoSLAMKF& kf)
 {
+    ensureUploaded();
     int32_t id = 0;
     if (sfe_bow_db_add(m_bow, kf.m_descriptors_left.ptr(0), kf.m_descriptors_left.rows, &id) != SFE_OK)
         throw std::runtime_error(std::string("sfe_bow_db_add: ") + sfe_last_error(m_ctx));
@@ -114,6 +127,7 @@ void CBoWManager::insertIntoDB(const CStereoSLAMKF& kf)
 void CBoWManager::queryDB(const CStereoSLAMKF& kf, QueryResults& ret, unsigned int num_results)
 {
     ret.clear();
+    ensureUploaded();
     std::vector<int32_t> ids(num_results); std::vector<double> sc(num_results); int32_t n = 0;
     if (sfe_bow_db_query(m_bow, kf.m_descriptors_left.ptr(0), kf.m_descriptors_left.rows, (int)num_results, ids.data(), sc.data(), &n) != SFE_OK)
         throw std::runtime_error(std::string("sfe_bow_db_query: ") + sfe_last_error(m_ctx));

@@ -41,8 +41,15 @@ public:
     CBoWManager() : m_ctx(nullptr), m_bow(nullptr) {}
     ~CBoWManager();
 
-    // CBoWManager.h:59-66 reads the file name from the ini (section, param) and loads it; here the two steps are
-    // split so that the class does not depend on mrpt::utils::CConfigFile.  The GPU context is the engine's.
+    // CBoWManager.h:59-66: reads the file name from [section] param of the ini (relative names are also tried next to the
+    // ini file) and loads it; throws if the file does not exist (ASSERT_FILE_EXISTS_, :63).  The reference calls this
+    // BEFORE the engine has seen an image (EST.cpp:1102 vs :112), i.e. before a GPU context exists: the vocabulary is
+    // parsed to host memory here and uploaded on the first insertIntoDB / queryDB, to the context given by setContext()
+    // or else to rso::CStereoOdometryEstimator::currentContext().
+    void loadVocabularyFromConfigFile(const mrpt::utils::CConfigFile& config, const std::string& section, const std::string& param);
+    void loadVocabulary(const std::string& voc_filename);
+    void setContext(sfe_context* ctx) { m_ctx = ctx; }
+    // round-1 forms (context given up front, uploaded immediately)
     void loadVocabulary(sfe_context* ctx, const std::string& voc_filename);
     void loadVocabularyFromConfigFile(sfe_context* ctx, const std::string& ini_file, const std::string& section, const std::string& param);
 
@@ -51,8 +58,10 @@ public:
     int size() const;
 
 private:
+    void ensureUploaded();
     sfe_context* m_ctx;
     sfe_bow* m_bow;
+    std::shared_ptr<TFlatVocabulary> m_host_voc;      // parsed, waiting for a context
 };
 
 // The brute-force part of CSRBAStereoSLAMEstimator::m_internal_data_association (EST.cpp:1432-1452): gathers the

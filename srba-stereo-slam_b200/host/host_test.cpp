@@ -31,10 +31,14 @@ int main(int argc, char** argv)
     t_vector_kf keyframes;
     std::ofstream out(argv[8], std::ios::binary);
     rso::CStereoOdometryEstimator::TStereoOdometryRequest req; rso::CStereoOdometryEstimator::TStereoOdometryResult res;
+    req.stereo_cam.leftCamera.ncols = req.stereo_cam.rightCamera.ncols = W; req.stereo_cam.leftCamera.nrows = req.stereo_cam.rightCamera.nrows = H;
+    req.stereo_cam.leftCamera.setIntrinsicParamsFromValues(707.0912 * W / 1241.0, 707.0912 * W / 1241.0, 601.8873 * W / 1241.0, 183.1104 * H / 376.0);      // synth.CorridorScene's pinhole
+    req.stereo_cam.rightCamera = req.stereo_cam.leftCamera; req.stereo_cam.rightCameraPose[0] = 0.54;
     for (int k = 0; k < NF; ++k) {
-        req.stereo_imgs.reset(new rso::CObservationStereoImages());
-        req.stereo_imgs->imageLeft = &frames[(size_t)(2 * k) * W * H]; req.stereo_imgs->imageRight = &frames[(size_t)(2 * k + 1) * W * H];
-        req.stereo_imgs->width = W; req.stereo_imgs->height = H; req.stereo_imgs->stride = W; req.repeat = false;
+        req.stereo_imgs = rso::CObservationStereoImagesPtr(new rso::CObservationStereoImages());       // what m_myCam.getNextFrame() yields (EST.cpp:44,79)
+        req.stereo_imgs->imageLeft.loadFromMemoryBuffer(W, H, false, &frames[(size_t)(2 * k) * W * H]);
+        req.stereo_imgs->imageRight.loadFromMemoryBuffer(W, H, false, &frames[(size_t)(2 * k + 1) * W * H]);
+        req.repeat = false;
         if (adaptive) {
             const int calls = processWithAdaptiveThresholds(vo, req, res, aopt);
             put(out, (int32_t)calls); put(out, (int32_t)vo.getFASTThreshold()); put(out, (int32_t)vo.getORBThreshold());

@@ -107,3 +107,26 @@ int srba_kf_load_file(const char* path, void* kpl, int* nl, void* kpr, int* nr, 
     return 0;
 }
 }
+
+// ---- options block -----------------------------------------------------------------------------------------------------
+#define SRBA_OPT_FIELDS(X, o) \
+    X(o.n_levels) X(o.n_feats) X(o.min_ORB_distance) X(o.detect_method) X(o.detect_fast_th) X(o.non_max_supp_method) \
+    X(o.matching_options.epipolar_TH) X(o.max_y_diff_epipolar) X(o.matching_options.maxORB_dist) X(o.max_orb_distance_da) \
+    X(o.ransac_fit_prob) X(o.matching_options.max_disp) X(o.matching_options.min_disp) X(o.matching_options.enable_robust_1to1_match) \
+    X(o.residual_th) X(o.max_translation) X(o.max_rotation) X(o.non_maximal_suppression) X(o.updated_matches_th) X(o.up_matches_th_plus)
+bool dumpOptionsToStream(std::ostream& stream, const TSRBAStereoSLAMOptions& options)
+{
+    if (!stream.good()) return false;
+#define X(f) wr(stream, f);
+    SRBA_OPT_FIELDS(X, options)
+#undef X
+    return stream.good();
+}
+bool loadOptionsFromStream(std::istream& stream, TSRBAStereoSLAMOptions& options)
+{
+    if (!stream.good()) return false;
+#define X(f) rd(stream, f);
+    SRBA_OPT_FIELDS(X, options)
+#undef X
+    return stream.good();
+}
