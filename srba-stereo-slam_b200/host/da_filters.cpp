@@ -148,11 +148,21 @@ static size_t count_tracked(const TVectorDAMatchInfo& m)
 void internalDataAssociation(rso::CStereoOdometryEstimator& voEngine, const TSRBAStereoSLAMOptions& o, const CStereoSLAMKF& this_kf,
                              const CStereoSLAMKF& other_kf, t_kf_da_info& out_da, const mrpt::poses::CPose3DRotVec& kf_ini_rel_pose)
 {
+    std::vector<cv::DMatch> bf;
+    matchKeyframes(voEngine.context(), this_kf, other_kf, bf);                          // EST.cpp:1432-1452 on the GPU
+    internalDataAssociationFromMatches(voEngine, o, this_kf, other_kf, bf, out_da, kf_ini_rel_pose, nullptr);
+}
+
+void internalDataAssociationFromMatches(rso::CStereoOdometryEstimator& voEngine, const TSRBAStereoSLAMOptions& o, const CStereoSLAMKF& this_kf,
+                                        const CStereoSLAMKF& other_kf, const std::vector<cv::DMatch>& bf_matches, t_kf_da_info& out_da,
+                                        const mrpt::poses::CPose3DRotVec& kf_ini_rel_pose, std::vector<int>* status_out)
+{
     const size_t this_num_matches = this_kf.m_matches.size();
     out_da.kf_idx = other_kf.m_kf_ID; out_da.tracked_matches = 0;
     out_da.tracking_info.assign(this_num_matches, std::make_pair(INVALID_IDX, 0.0));
     TVectorDAMatchInfo this_matches(this_num_matches);
-    matchKeyframes(voEngine.context(), this_kf, other_kf, this_matches.m_matches);      // EST.cpp:1432-1452 on the GPU
+    this_matches.m_matches = bf_matches;
+    if (status_out) status_out->assign(this_num_matches, (int)TVectorDAMatchInfo::sTRACKED);
     if (this_matches.m_matches.size() != this_num_matches) return;                      // empty train set: BFMatcher returns no matches
     const std::string sep = general_options.out_dir + SRBA_PATH_SEP;
     if (general_options.debug) {                                                        // if_raw_match_kfXXXX_with_kfYYYY.txt, EST.cpp:1454-1473
@@ -180,6 +190,7 @@ void internalDataAssociation(rso::CStereoOdometryEstimator& voEngine, const TSRB
         else { detectOutliersWithChangeInPose(voEngine, this_matches, this_kf, other_kf, kf_ini_rel_pose, o.stereo_camera, o.residual_th); inliers = count_tracked(this_matches); }
     }
     VERBOSE_LEVEL(2) << "[iDA " << this_kf.m_kf_ID << "->" << other_kf.m_kf_ID << "]: Final number of inliers: " << inliers << "/" << this_num_matches << std::endl;
+    if (status_out) for (size_t k = 0; k < this_num_matches; ++k) (*status_out)[k] = (int)this_matches.m_status[k];
     if (invalid) return;
     FILE* f2 = nullptr;
     if (general_options.debug) {                                                        // if_match_after_kfXXXX_with_kfYYYY.txt, EST.cpp:1650-1689

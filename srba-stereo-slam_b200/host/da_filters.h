@@ -62,6 +62,10 @@ void detectOutliersWithChangeInPose(rso::CStereoOdometryEstimator& voEngine, TVe
 void internalDataAssociation(rso::CStereoOdometryEstimator& voEngine, const TSRBAStereoSLAMOptions& srba_options, const CStereoSLAMKF& this_kf,
                              const CStereoSLAMKF& other_kf, t_kf_da_info& out_da,
                              const mrpt::poses::CPose3DRotVec& kf_ini_rel_pose = mrpt::poses::CPose3DRotVec());
+// The same from a ready brute-force result (what the GPU match returned): everything after EST.cpp:1452.
+void internalDataAssociationFromMatches(rso::CStereoOdometryEstimator& voEngine, const TSRBAStereoSLAMOptions& srba_options, const CStereoSLAMKF& this_kf,
+                                        const CStereoSLAMKF& other_kf, const std::vector<cv::DMatch>& bf_matches, t_kf_da_info& out_da,
+                                        const mrpt::poses::CPose3DRotVec& kf_ini_rel_pose, std::vector<int>* status_out = nullptr);
 // CSRBAStereoSLAMEstimator::m_data_association (EST.cpp:1341-1411): one record per similar keyframe, in list order.
 void dataAssociation(rso::CStereoOdometryEstimator& voEngine, const TSRBAStereoSLAMOptions& srba_options, const t_vector_kf& keyframes,
                      const CStereoSLAMKF& kf, const TLoopClosureInfo& lc_info, TVectorKfsDaInfo& out_da);

@@ -202,7 +202,7 @@ class CPose3D {
 public:
     CPose3D() { setFromValues(0, 0, 0, 0, 0, 0); }
     CPose3D(double x, double y, double z, double yaw = 0, double pitch = 0, double roll = 0) { setFromValues(x, y, z, yaw, pitch, roll); }
-    explicit CPose3D(const CPose3DRotVec& p);
+    CPose3D(const CPose3DRotVec& p);            // implicit, as the reference relies on (EST.cpp:1765, 1850)
     void setFromValues(double x, double y, double z, double yaw, double pitch, double roll)
     {
         m_coords[0] = x; m_coords[1] = y; m_coords[2] = z;

@@ -25,6 +25,16 @@ sfe_context* CStereoOdometryEstimator::currentContext()
     return nullptr;
 }
 
+// cv::BFMatcher(NORM_HAMMING).match of cv_compat.h -> sfe_match_bf on the newest engine's context
+static int gpu_brute_force_hook(const uint8_t* q, int nq, const uint8_t* t, int nt, cv::DMatch* out)
+{
+    sfe_context* ctx = CStereoOdometryEstimator::currentContext();
+    if (!ctx) return -1;
+    int32_t n = 0;
+    static_assert(sizeof(cv::DMatch) == sizeof(sfe_dmatch), "DMatch layout");
+    return sfe_match_bf(ctx, q, nq, t, nt, reinterpret_cast<sfe_dmatch*>(out), &n) == SFE_OK ? (int)n : -1;
+}
+
 // Keys of SURVEY.md Appendix B that parameterise the hot path; a section is only read if the caller lists it (EST.cpp:1122-1131).
 void CStereoOdometryEstimator::loadParamsFromConfigFile(const mrpt::utils::CConfigFile& cfg, const std::vector<std::string>& sections)
 {
@@ -102,6 +112,9 @@ bool CStereoOdometryEstimator::ensureContext(int width, int height)
     cfg.max_pairs = 1; cfg.device = device;
     if (sfe_create(&cfg, &m_ctx) != SFE_OK) { m_err = sfe_last_error(nullptr); m_ctx = nullptr; return false; }
     m_w = width; m_h = height;
+#ifndef SRBA_B200_WITH_OPENCV
+    cv::bruteForceHook() = &gpu_brute_force_hook;
+#endif
     return true;
 }
 
