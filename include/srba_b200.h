@@ -140,7 +140,7 @@ int sfe_download_batch(sfe_context* ctx, const sfe_keypoint** kps, const uint8_t
 
 /* Streaming form of sfe_process_batch_host + sfe_download_batch: submit enqueues H2D copy, all kernels and the
  * D2H copy of the results on sfe_stream() and returns at once; wait blocks until they have landed in the
- * context's pinned result buffers (same layout as sfe_download_batch).  Two contexts used alternately overlap
+ * context's pinned result buffers (same layout as sfe_download_batch; entries beyond an image's count are unspecified).  Two contexts used alternately overlap
  * one batch's PCIe traffic with the other's kernels.  `images` should be pinned (sfe_host_staging). */
 int sfe_submit_batch_host(sfe_context* ctx, const uint8_t* images, int npairs, size_t stride, size_t image_stride);
 int sfe_wait_batch(sfe_context* ctx, const sfe_keypoint** kps, const uint8_t** desc,
@@ -206,6 +206,11 @@ int sfe_num_stages(void);
 const char* sfe_stage_name(int stage);
 int sfe_stage_times(sfe_context* ctx, float* ms /* sfe_num_stages() */, int32_t* launches);
 int64_t sfe_kernel_launches(const sfe_context* ctx);   /* kernels launched (or replayed) so far  */
+/* The downloads ship content, not capacity (the first ~nfeatures slots of every image, the recent maximum of matches per
+ * pair; a remainder is fetched by sfe_wait_batch when a count exceeds what was shipped).  Bytes the last download moved,
+ * and how often a remainder had to be fetched so far. */
+int64_t sfe_last_d2h_bytes(const sfe_context* ctx);
+int64_t sfe_d2h_refetches(const sfe_context* ctx);
 
 /* ---- bag of words ----------------------------------------------------------------------------
  * Replaces: CBoWManager (CBoWManager.h:44-111) = DBoW2 BriefVocabulary + BriefDatabase.
@@ -251,6 +256,28 @@ int  sfe_kfdb_process_batch_on(sfe_kfdb* db, sfe_context* src, int npairs);
 int  sfe_kfdb_results(sfe_kfdb* db, const int32_t** query_ids /* [n][4] */, const double** query_scores /* [n][4] */,
                       const int32_t** query_n /* [n] */, const int32_t** pair_kf /* [n][5] */,
                       const uint32_t** best /* [n][5][capacity] */, const int32_t** matched_n /* [n] */);
+
+/* Streaming download of the last queried batch's results: submit enqueues the D2H copies behind the kernels (one of 4
+ * pinned slots, `best` ships the filled prefix of every association row, not the capacity) and returns at once; wait
+ * blocks until that slot has landed.  Layout as sfe_kfdb_results. */
+int  sfe_kfdb_submit_results(sfe_kfdb* db, int32_t* slot_out);
+int  sfe_kfdb_wait_results(sfe_kfdb* db, int slot, const int32_t** query_ids, const double** query_scores, const int32_t** query_n,
+                           const int32_t** pair_kf, const uint32_t** best, const int32_t** matched_n, int32_t* n_frames);
+
+/* ---- one logical keyframe database across the GPUs of a box (BASELINE.json configs[2]: frames sharded over 2/4/8 GPUs) -------
+ * The reference has ONE database (CBoWManager.h:71-88, queried at EST.cpp:424-427, matched at :1432-1452); with the frames
+ * sharded over ranks, rank r owns the global keyframes [starts[r], starts[r+1]) in its own stores.  Every rank exports its five
+ * store arrays (matched-subset descriptors + counts, BoW words + values + counts) with sfe_ipc_export, maps its peers' with
+ * sfe_ipc_import and hands the pointers over; the score / pair / brute-force kernels then read older keyframes of other ranks
+ * IN-KERNEL through NVLink -- nothing is replicated, only the blocks a query touches cross the link.
+ * A frame with global index g still only sees entries < g, so the results are identical to one rank processing the whole
+ * sequence; that takes two passes: every rank first inserts all its frames (sfe_kfdb_insert_batch_on), a barrier, then queries
+ * them (sfe_kfdb_query_batch_on).  ptrs: nranks x 5 device pointers in the order of sfe_kfdb_store_pointers (the own rank's
+ * row is ignored). */
+int  sfe_kfdb_store_pointers(sfe_kfdb* db, void* out[5]);
+int  sfe_kfdb_set_peers(sfe_kfdb* db, int nranks, int rank, const int32_t* starts /* nranks+1 */, const void* const* ptrs /* nranks*5 */);
+int  sfe_kfdb_insert_batch_on(sfe_kfdb* db, sfe_context* src, int npairs);                    /* append src's last stereo batch */
+int  sfe_kfdb_query_batch_on(sfe_kfdb* db, sfe_context* stream_ctx, int first_local_frame, int npairs);
 
 #ifdef __cplusplus
 }

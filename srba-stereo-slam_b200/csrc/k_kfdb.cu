@@ -20,7 +20,25 @@
 #define KF_QT 32                 // queries per score CTA (bitmaps in shared memory, one per lane)
 #define KF_PAIRS 5               // previous keyframe + 4 BoW hits (EST.cpp:426, :1758)
 
-struct BfPair { int q_start, nq, t_start, nt, out_start; };
+#define KF_MAX_RANKS 16
+#define KF_RESULT_SLOTS 4
+
+struct BfPair { int q_start, nq, t_rank, t_start, nt, out_start; };
+
+// One logical keyframe database over the GPUs of a box: rank r owns the global entries [start[r], start[r+1]) in its own
+// stores; the other ranks' stores are mapped with CUDA IPC and read in-kernel through NVLink (no replication).
+struct KfPeers {
+    const uint8_t* msub[KF_MAX_RANKS]; const int32_t* msub_n[KF_MAX_RANKS];
+    const int32_t* dbw[KF_MAX_RANKS]; const double* dbv[KF_MAX_RANKS]; const int32_t* dbn[KF_MAX_RANKS];
+    int start[KF_MAX_RANKS + 1]; int nranks;
+};
+__device__ __forceinline__ int kf_rank_of(const KfPeers& P, int e)
+{
+    int r = 0;
+#pragma unroll 1
+    while (r + 1 < P.nranks && e >= P.start[r + 1]) ++r;
+    return r;
+}
 
 struct sfe_kfdb {
     sfe_context* ctx = nullptr; sfe_bow* bow = nullptr;
@@ -36,6 +54,11 @@ struct sfe_kfdb {
     int32_t* h_msub_n = nullptr;
     int last_base = 0, last_n = 0;
     cudaEvent_t ev_done = nullptr; bool ev_valid = false; cudaStream_t last_stream = nullptr;
+    // multi-rank view (defaults: one rank, own stores)
+    KfPeers peers; int rank = 0; int total_frames = 0;            // total_frames: score stride = capacity of the whole logical database
+    // asynchronous result slots (sfe_kfdb_submit_results / sfe_kfdb_wait_results)
+    struct Slot { int32_t* qid; double* qscore; int32_t* qn; int32_t* pair_kf; uint32_t* best; int32_t* msub_n; cudaEvent_t ev; int n; int ship; } slot[KF_RESULT_SLOTS] = {};
+    int next_slot = 0; int ship_m = 0;
 };
 
 #define KF_CUDA(d, call) SFE_CUDA((d)->ctx, call)
@@ -199,7 +222,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)      // ou
 }
 
 __global__ void __launch_bounds__(KS_WARPS * 32, 6)
-kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv, const int32_t* __restrict__ dbn, int cap,
+kf_score_kernel(const __grid_constant__ KfPeers P, int cap,
                 int base, int nq, int nwords, const uint32_t* __restrict__ tmask, const double* __restrict__ dense,
                 int score_stride, double* __restrict__ score, int32_t* __restrict__ common, int ntiles, int n_items,
                 int* __restrict__ work_ctr)
@@ -221,9 +244,10 @@ kf_score_kernel(const int32_t* __restrict__ dbw, const double* __restrict__ dbv,
         const uint32_t* __restrict__ T = tmask + (size_t)tile * nwords;
         const int q = q0 + lane;
         const double* __restrict__ myq = dense + (size_t)min(q, nq - 1) * nwords;
-        const int n = dbn[e];
-        const int32_t* ew = dbw + (size_t)e * cap;
-        const double* ev = dbv + (size_t)e * cap;
+        const int er = kf_rank_of(P, e), le = e - P.start[er];        // owner rank and its local entry index
+        const int n = P.dbn[er][le];
+        const int32_t* ew = P.dbw[er] + (size_t)le * cap;
+        const double* ev = P.dbv[er] + (size_t)le * cap;
         double s = 0.0; bool any = false;
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int i = c0 + lane;
@@ -293,8 +317,9 @@ kf_topk_kernel(const double* __restrict__ score, int32_t* __restrict__ common, i
 }
 
 // ---- 7. pair list: previous keyframe + BoW hits (without duplicates of the previous keyframe) ---------------------
-__global__ void kf_pairs_kernel(const int32_t* __restrict__ qid, const int32_t* __restrict__ qn, const int32_t* __restrict__ msub_n,
-                                int base, int nq, int cap, BfPair* __restrict__ pairs, int32_t* __restrict__ pair_kf)
+__global__ void kf_pairs_kernel(const __grid_constant__ KfPeers P, const int32_t* __restrict__ qid, const int32_t* __restrict__ qn,
+                                int base /* global id of query 0 */, int lbase /* its local store index */, int nq, int cap,
+                                BfPair* __restrict__ pairs, int32_t* __restrict__ pair_kf, int my_rank)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq * KF_PAIRS) return;
@@ -303,8 +328,9 @@ __global__ void kf_pairs_kernel(const int32_t* __restrict__ qid, const int32_t* 
     if (slot == 0) kf = g - 1;                                                         // may be -1 for the very first frame
     else if (slot - 1 < qn[q]) { kf = qid[q * 4 + slot - 1]; if (kf == g - 1) kf = -1; }
     BfPair pr;
-    pr.q_start = g * cap; pr.nq = kf >= 0 ? msub_n[g] : 0;
-    pr.t_start = max(kf, 0) * cap; pr.nt = kf >= 0 ? msub_n[kf] : 0;
+    pr.q_start = (lbase + q) * cap; pr.nq = kf >= 0 ? P.msub_n[my_rank][lbase + q] : 0;
+    const int tr = kf >= 0 ? kf_rank_of(P, kf) : 0, tl = max(kf, 0) - P.start[tr];
+    pr.t_rank = tr; pr.t_start = tl * cap; pr.nt = kf >= 0 ? P.msub_n[tr][tl] : 0;
     pr.out_start = i * cap;
     pairs[i] = pr; pair_kf[i] = kf;
 }
@@ -314,7 +340,7 @@ __global__ void kf_pairs_kernel(const int32_t* __restrict__ qid, const int32_t* 
 #define KBF_CHUNK 128
 #define KBF_SPLITS 4
 __global__ void __launch_bounds__(KBF_THREADS)
-kf_bf_kernel(const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs, uint32_t* __restrict__ best)
+kf_bf_kernel(const __grid_constant__ KfPeers P, const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs, uint32_t* __restrict__ best)
 {
     __shared__ uint4 ts[KBF_CHUNK * 2];
     const BfPair pr = pairs[blockIdx.z];
@@ -329,7 +355,7 @@ kf_bf_kernel(const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs
         const uint4* qp = reinterpret_cast<const uint4*>(store + (size_t)(pr.q_start + q) * 32);
         q0 = __ldg(qp); q1 = __ldg(qp + 1);
     }
-    const uint4* tp = reinterpret_cast<const uint4*>(store + (size_t)pr.t_start * 32);
+    const uint4* tp = reinterpret_cast<const uint4*>(P.msub[pr.t_rank] + (size_t)pr.t_start * 32);   // possibly a peer GPU's store (NVLink)
     uint32_t key = 0xffffffffu;
     for (int c0 = t0; c0 < t1; c0 += KBF_CHUNK) {
         const int n = min(KBF_CHUNK, t1 - c0);
@@ -346,6 +372,23 @@ kf_bf_kernel(const uint8_t* __restrict__ store, const BfPair* __restrict__ pairs
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
+static void kf_default_peers(sfe_kfdb* d)
+{
+    memset(&d->peers, 0, sizeof(d->peers));
+    d->peers.nranks = 1; d->rank = 0;
+    d->peers.msub[0] = d->d_msub; d->peers.msub_n[0] = d->d_msub_n; d->peers.dbw[0] = d->d_dbw; d->peers.dbv[0] = d->d_dbv; d->peers.dbn[0] = d->d_dbn;
+    d->peers.start[0] = 0; d->peers.start[1] = 0x7fffffff;
+}
+
+static cudaError_t kf_alloc_scores(sfe_kfdb* d, int total_frames)
+{
+    cudaFree(d->d_score); cudaFree(d->d_common); d->d_score = nullptr; d->d_common = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d->d_score, (size_t)d->B * total_frames * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d->d_common, (size_t)d->B * total_frames * 4);
+    if (e == cudaSuccess) d->total_frames = total_frames;
+    return e;
+}
+
 extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_frames, sfe_kfdb** out)
 {
     SFE_BIND_DEVICE(ctx);
@@ -361,20 +404,29 @@ extern "C" int sfe_kfdb_create(sfe_context* ctx, sfe_bow* bow, int capacity_fram
     al((void**)&d->d_dbw, F * S * 4); al((void**)&d->d_dbv, F * S * 8); al((void**)&d->d_dbn, F * 4);
     al((void**)&d->d_word, B * S * 4); al((void**)&d->d_weight, B * S * 8);
     al((void**)&d->d_tmask, (size_t)d->ntiles * d->nwords * 4); al((void**)&d->d_dense, B * (size_t)d->nwords * 8);
-    al((void**)&d->d_score, B * F * 8); al((void**)&d->d_common, B * F * 4); al((void**)&d->d_work_ctr, 256);
+    al((void**)&d->d_work_ctr, 256);
     al((void**)&d->d_qid, B * 4 * 4); al((void**)&d->d_qscore, B * 4 * 8); al((void**)&d->d_qn, B * 4);
     al((void**)&d->d_pairs, B * KF_PAIRS * sizeof(BfPair)); al((void**)&d->d_pair_kf, B * KF_PAIRS * 4);
     al((void**)&d->d_best, B * KF_PAIRS * S * 4);
+    if (e == cudaSuccess) e = kf_alloc_scores(d, capacity_frames);
     ah((void**)&d->h_qid, B * 4 * 4); ah((void**)&d->h_qscore, B * 4 * 8); ah((void**)&d->h_qn, B * 4);
     ah((void**)&d->h_pair_kf, B * KF_PAIRS * 4); ah((void**)&d->h_best, B * KF_PAIRS * S * 4); ah((void**)&d->h_msub_n, B * 4);
+    for (int k = 0; k < KF_RESULT_SLOTS; ++k) {
+        sfe_kfdb::Slot& sl = d->slot[k];
+        ah((void**)&sl.qid, B * 4 * 4); ah((void**)&sl.qscore, B * 4 * 8); ah((void**)&sl.qn, B * 4); ah((void**)&sl.pair_kf, B * KF_PAIRS * 4);
+        ah((void**)&sl.best, B * KF_PAIRS * S * 4); ah((void**)&sl.msub_n, B * 4);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemset(d->d_tmask, 0, (size_t)d->ntiles * d->nwords * 4);
     if (e == cudaSuccess) e = cudaMemset(d->d_dense, 0, B * (size_t)d->nwords * 8);
     if (e == cudaSuccess) e = cudaMemset(d->d_msub_n, 0, F * 4);
     if (e == cudaSuccess) e = cudaMemset(d->d_dbn, 0, F * 4);
     if (e != cudaSuccess) { ctx->err = std::string("sfe_kfdb_create: ") + cudaGetErrorString(e); sfe_kfdb_destroy(d); return SFE_ERR_CUDA; }
-    cudaFuncSetAttribute(kf_vector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
+    sfe_raise_dynamic_smem((const void*)kf_vector_kernel, ctx->cfg.device, 32768 * 4);
     cudaGetLastError();
+    kf_default_peers(d);
+    d->ship_m = std::min((int)S, ctx->cfg.nfeatures + 16);
     *out = d;
     return SFE_OK;
 }
@@ -389,6 +441,11 @@ extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
     cudaFree(d->d_pair_kf); cudaFree(d->d_best);
     cudaFreeHost(d->h_qid); cudaFreeHost(d->h_qscore); cudaFreeHost(d->h_qn); cudaFreeHost(d->h_pair_kf); cudaFreeHost(d->h_best);
     cudaFreeHost(d->h_msub_n);
+    for (int k = 0; k < KF_RESULT_SLOTS; ++k) {
+        sfe_kfdb::Slot& sl = d->slot[k];
+        cudaFreeHost(sl.qid); cudaFreeHost(sl.qscore); cudaFreeHost(sl.qn); cudaFreeHost(sl.pair_kf); cudaFreeHost(sl.best); cudaFreeHost(sl.msub_n);
+        if (sl.ev) cudaEventDestroy(sl.ev);
+    }
     if (d->ev_done) cudaEventDestroy(d->ev_done);
     delete d;
 }
@@ -396,58 +453,125 @@ extern "C" void sfe_kfdb_destroy(sfe_kfdb* d)
 extern "C" int sfe_kfdb_size(const sfe_kfdb* d) { return d ? d->n_frames : 0; }
 extern "C" int sfe_kfdb_reset(sfe_kfdb* d) { if (!d) return SFE_ERR_INVALID; d->n_frames = 0; return SFE_OK; }
 
-extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* src, int npairs);
-
-extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
+// ---- one logical database over several GPUs ----------------------------------------------------------------------------------
+extern "C" int sfe_kfdb_store_pointers(sfe_kfdb* d, void* out[5])
 {
-    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
-    return d ? sfe_kfdb_process_batch_on(d, d->ctx, npairs) : SFE_ERR_INVALID;
+    if (!d || !out) return SFE_ERR_INVALID;
+    out[0] = d->d_msub; out[1] = d->d_msub_n; out[2] = d->d_dbw; out[3] = d->d_dbv; out[4] = d->d_dbn;
+    return SFE_OK;
 }
 
-// Runs on the SOURCE context's stream (so that context's next batch cannot overwrite the descriptors being read);
-// batches from different contexts are serialised on the database through an event.
-extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs)
+extern "C" int sfe_kfdb_set_peers(sfe_kfdb* d, int nranks, int rank, const int32_t* starts, const void* const* ptrs)
 {
     SFE_BIND_DEVICE((d ? d->ctx : nullptr));
+    if (!d) return SFE_ERR_INVALID;
+    if (nranks < 1 || nranks > KF_MAX_RANKS || rank < 0 || rank >= nranks || !starts || !ptrs) { d->ctx->err = "sfe_kfdb_set_peers: bad arguments"; return SFE_ERR_INVALID; }
+    for (int r = 0; r < nranks; ++r) if (starts[r + 1] < starts[r] || (r == rank && starts[r + 1] - starts[r] > d->cap_frames)) { d->ctx->err = "sfe_kfdb_set_peers: shard does not fit the local store"; return SFE_ERR_INVALID; }
+    KF_CUDA(d, cudaStreamSynchronize(d->last_stream ? d->last_stream : d->ctx->stream));
+    memset(&d->peers, 0, sizeof(d->peers));
+    d->peers.nranks = nranks; d->rank = rank;
+    for (int r = 0; r < nranks; ++r) {
+        const void* const* p = ptrs + 5 * r;
+        d->peers.msub[r] = (const uint8_t*)(r == rank ? d->d_msub : p[0]); d->peers.msub_n[r] = (const int32_t*)(r == rank ? d->d_msub_n : p[1]);
+        d->peers.dbw[r] = (const int32_t*)(r == rank ? d->d_dbw : p[2]); d->peers.dbv[r] = (const double*)(r == rank ? d->d_dbv : p[3]);
+        d->peers.dbn[r] = (const int32_t*)(r == rank ? d->d_dbn : p[4]);
+        d->peers.start[r] = starts[r];
+    }
+    d->peers.start[nranks] = starts[nranks];
+    if (starts[nranks] > d->total_frames) {
+        const cudaError_t e = kf_alloc_scores(d, starts[nranks]);
+        if (e != cudaSuccess) { d->ctx->err = std::string("sfe_kfdb_set_peers: ") + cudaGetErrorString(e); return SFE_ERR_CUDA; }
+    }
+    return SFE_OK;
+}
+
+static int kf_check_src(sfe_kfdb* d, sfe_context* c, int npairs)
+{
     if (!d || !c || npairs < 1 || npairs > d->B) return SFE_ERR_INVALID;
     if (c->pack.kp_cap != d->stride || c->cfg.device != d->ctx->cfg.device) { c->err = "source context does not match the keyframe database"; return SFE_ERR_INVALID; }
+    return SFE_OK;
+}
+
+// Pass 1 (steps 1-3): append every pair of the source context's last stereo batch to the LOCAL stores.
+static int kf_insert(sfe_kfdb* d, sfe_context* c, int npairs, cudaStream_t s)
+{
     sfe_bow* b = d->bow;
-    if (!c->have_results || c->last_npairs < npairs) { c->err = "sfe_kfdb_process_batch: process the stereo batch first"; return SFE_ERR_STATE; }
+    if (!c->have_results || c->last_npairs < npairs) { c->err = "sfe_kfdb: process the stereo batch first"; return SFE_ERR_STATE; }
     if (d->n_frames + npairs > d->cap_frames) { c->err = "keyframe store is full"; return SFE_ERR_CAPACITY; }
-    cudaStream_t s = c->stream;
-    if (d->ev_valid && d->last_stream != s) KF_CUDA(d, cudaStreamWaitEvent(s, d->ev_done, 0));
-    const int cap = d->stride, base = d->n_frames, E = base + npairs;
-    // 1. matched-subset descriptors -> store
+    const int cap = d->stride, base = d->n_frames;
     kf_gather_kernel<<<dim3((cap + 127) / 128, npairs), 256, 0, s>>>(c->d_desc, c->d_matches, c->d_match_count, cap, base, d->d_msub, d->d_msub_n);
-    // 2. words, 3. BoW vectors (into the database slots base .. base+npairs-1)
     kf_transform_kernel<<<dim3((cap * 8 + 255) / 256, npairs), 256, 0, s>>>(b->d_first, b->d_nchild, b->d_desc, b->d_word, b->d_weight, b->depth,
                                                                             c->d_desc, c->d_kp_count, cap, d->d_word, d->d_weight);
     int np2 = 1; while (np2 < cap) np2 <<= 1;
     if (np2 > 32768) { c->err = "keypoint capacity too large for the BoW vector kernel"; return SFE_ERR_INVALID; }
     kf_vector_kernel<<<npairs, KV_THREADS, (size_t)np2 * 4, s>>>(d->d_word, d->d_weight, c->d_kp_count, cap, np2, base, d->d_dbw, d->d_dbv, d->d_dbn);
-    // 4-6. query: every frame against the entries older than itself
-    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->d_tmask, d->d_dense, 0);
-    const int ne_vis = E - 1;                                   // entries any query of this batch can see
+    c->launches += 3;
+    d->n_frames = base + npairs;
+    return SFE_OK;
+}
+
+// Pass 2 (steps 4-8): query + associate the local frames [lbase, lbase + npairs) against every OLDER entry of the logical
+// database (all ranks), top 4, pair list, brute force.
+static int kf_query(sfe_kfdb* d, sfe_context* c, int lbase, int npairs, cudaStream_t s)
+{
+    if (lbase < 0 || lbase + npairs > d->n_frames) { c->err = "sfe_kfdb_query: frames not in the store"; return SFE_ERR_INVALID; }
+    const int cap = d->stride, gbase = d->peers.start[d->rank] + lbase;
+    if (gbase + npairs > d->total_frames) { c->err = "sfe_kfdb_query: score buffer smaller than the logical database"; return SFE_ERR_CAPACITY; }
+    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, lbase, d->nwords, d->d_tmask, d->d_dense, 0);
+    const int ne_vis = gbase + npairs - 1;                      // entries any query of this batch can see
     if (ne_vis > 0) {
         const int tiles = (npairs + KF_QT - 1) / KF_QT;
         const int n_items = ne_vis * tiles;
         const int gx = std::max(1, std::min((n_items + KS_WARPS - 1) / KS_WARPS, 148 * 6));       // persistent: 6 CTAs per SM
         KF_CUDA(d, cudaMemsetAsync(d->d_work_ctr, 0, sizeof(int), s));
-        kf_score_kernel<<<gx, KS_WARPS * 32, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, npairs, d->nwords, d->d_tmask, d->d_dense,
-                                                     d->cap_frames, d->d_score, d->d_common, tiles, n_items, d->d_work_ctr);
+        kf_score_kernel<<<gx, KS_WARPS * 32, 0, s>>>(d->peers, cap, gbase, npairs, d->nwords, d->d_tmask, d->d_dense,
+                                                     d->total_frames, d->d_score, d->d_common, tiles, n_items, d->d_work_ctr);
     }
-    kf_topk_kernel<<<npairs, 256, 0, s>>>(d->d_score, d->d_common, base, d->cap_frames, 4, d->d_qid, d->d_qscore, d->d_qn);
-    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, base, d->nwords, d->d_tmask, d->d_dense, 1);
-    // 7-8. data association: previous keyframe + BoW hits
-    kf_pairs_kernel<<<(npairs * KF_PAIRS + 127) / 128, 128, 0, s>>>(d->d_qid, d->d_qn, d->d_msub_n, base, npairs, cap, d->d_pairs, d->d_pair_kf);
+    kf_topk_kernel<<<npairs, 256, 0, s>>>(d->d_score, d->d_common, gbase, d->total_frames, 4, d->d_qid, d->d_qscore, d->d_qn);
+    kf_query_prep_kernel<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(d->d_dbw, d->d_dbv, d->d_dbn, cap, lbase, d->nwords, d->d_tmask, d->d_dense, 1);
+    kf_pairs_kernel<<<(npairs * KF_PAIRS + 127) / 128, 128, 0, s>>>(d->peers, d->d_qid, d->d_qn, gbase, lbase, npairs, cap, d->d_pairs, d->d_pair_kf, d->rank);
     KF_CUDA(d, cudaMemsetAsync(d->d_best, 0xff, (size_t)npairs * KF_PAIRS * cap * 4, s));
-    kf_bf_kernel<<<dim3((cap + KBF_THREADS - 1) / KBF_THREADS, KBF_SPLITS, npairs * KF_PAIRS), KBF_THREADS, 0, s>>>(d->d_msub, d->d_pairs, d->d_best);
-    c->launches += ne_vis > 0 ? 9 : 8;
+    kf_bf_kernel<<<dim3((cap + KBF_THREADS - 1) / KBF_THREADS, KBF_SPLITS, npairs * KF_PAIRS), KBF_THREADS, 0, s>>>(d->peers, d->d_msub, d->d_pairs, d->d_best);
+    c->launches += ne_vis > 0 ? 6 : 5;
+    d->last_base = lbase; d->last_n = npairs;
+    return SFE_OK;
+}
+
+extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* src, int npairs);
+extern "C" int sfe_kfdb_process_batch(sfe_kfdb* d, int npairs)
+{
+    return d ? sfe_kfdb_process_batch_on(d, d->ctx, npairs) : SFE_ERR_INVALID;
+}
+
+// mode bit 0: insert, bit 1: query.  Runs on the SOURCE context's stream (so that context's next batch cannot overwrite the
+// descriptors being read); batches from different contexts are serialised on the database through an event.
+static int kf_run(sfe_kfdb* d, sfe_context* c, int lbase, int npairs, int mode)
+{
+    int r = kf_check_src(d, c, npairs); if (r) return r;
+    cudaStream_t s = c->stream;
+    if (d->ev_valid && d->last_stream != s) KF_CUDA(d, cudaStreamWaitEvent(s, d->ev_done, 0));
+    if (mode & 1) { lbase = d->n_frames; r = kf_insert(d, c, npairs, s); if (r) return r; }
+    if (mode & 2) { r = kf_query(d, c, lbase, npairs, s); if (r) return r; }
     KF_CUDA(d, cudaGetLastError());
     KF_CUDA(d, cudaEventRecord(d->ev_done, s));
     d->ev_valid = true; d->last_stream = s;
-    d->last_base = base; d->last_n = npairs; d->n_frames = E;
     return SFE_OK;
+}
+
+extern "C" int sfe_kfdb_process_batch_on(sfe_kfdb* d, sfe_context* c, int npairs)
+{
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
+    return kf_run(d, c, 0, npairs, 3);
+}
+extern "C" int sfe_kfdb_insert_batch_on(sfe_kfdb* d, sfe_context* c, int npairs)
+{
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
+    return kf_run(d, c, 0, npairs, 1);
+}
+extern "C" int sfe_kfdb_query_batch_on(sfe_kfdb* d, sfe_context* c, int first_local_frame, int npairs)
+{
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
+    return kf_run(d, c, first_local_frame, npairs, 2);
 }
 
 extern "C" int sfe_kfdb_results(sfe_kfdb* d, const int32_t** query_ids, const double** query_scores, const int32_t** query_n,
@@ -466,5 +590,51 @@ extern "C" int sfe_kfdb_results(sfe_kfdb* d, const int32_t** query_ids, const do
     KF_CUDA(d, cudaStreamSynchronize(s));
     if (query_ids) *query_ids = d->h_qid; if (query_scores) *query_scores = d->h_qscore; if (query_n) *query_n = d->h_qn;
     if (pair_kf) *pair_kf = d->h_pair_kf; if (best) *best = d->h_best; if (matched_n) *matched_n = d->h_msub_n;
+    return SFE_OK;
+}
+
+// Streaming form: enqueue the download of the last queried batch's results right behind its kernels (same stream), into one of
+// KF_RESULT_SLOTS pinned slots; the next batch may overwrite the device buffers as soon as this copy has run.  `best` ships the
+// first ship_m slots of every association row (content, not capacity); a remainder is fetched by the wait if a frame had more matches.
+extern "C" int sfe_kfdb_submit_results(sfe_kfdb* d, int32_t* slot_out)
+{
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
+    if (!d || !slot_out) return SFE_ERR_INVALID;
+    if (d->last_n == 0 || !d->last_stream) { d->ctx->err = "no batch processed"; return SFE_ERR_STATE; }
+    const int k = d->next_slot; d->next_slot = (k + 1) % KF_RESULT_SLOTS;
+    sfe_kfdb::Slot& sl = d->slot[k];
+    cudaStream_t s = d->last_stream; const int n = d->last_n; const size_t cap = d->stride;
+    KF_CUDA(d, cudaMemcpyAsync(sl.qid, d->d_qid, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(sl.qscore, d->d_qscore, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(sl.qn, d->d_qn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(sl.pair_kf, d->d_pair_kf, sizeof(int32_t) * KF_PAIRS * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpyAsync(sl.msub_n, d->d_msub_n + d->last_base, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaMemcpy2DAsync(sl.best, cap * 4, d->d_best, cap * 4, (size_t)d->ship_m * 4, (size_t)KF_PAIRS * n, cudaMemcpyDeviceToHost, s));
+    KF_CUDA(d, cudaEventRecord(sl.ev, s));
+    KF_CUDA(d, cudaEventRecord(d->ev_done, s));              // the next batch's kernels (any stream) wait for this copy too
+    sl.n = n; sl.ship = d->ship_m;
+    *slot_out = k;
+    return SFE_OK;
+}
+
+extern "C" int sfe_kfdb_wait_results(sfe_kfdb* d, int slot, const int32_t** query_ids, const double** query_scores, const int32_t** query_n,
+                                     const int32_t** pair_kf, const uint32_t** best, const int32_t** matched_n, int32_t* n_frames)
+{
+    SFE_BIND_DEVICE((d ? d->ctx : nullptr));
+    if (!d || slot < 0 || slot >= KF_RESULT_SLOTS) return SFE_ERR_INVALID;
+    sfe_kfdb::Slot& sl = d->slot[slot];
+    if (sl.n == 0) { d->ctx->err = "sfe_kfdb_wait_results: empty slot"; return SFE_ERR_STATE; }
+    KF_CUDA(d, cudaEventSynchronize(sl.ev));
+    int mmax = 0; for (int i = 0; i < sl.n; ++i) mmax = std::max(mmax, std::min(sl.msub_n[i], d->stride));
+    if (mmax > sl.ship) {
+        // mis-speculation: the rows are still in d_best only if no later batch has been queried -- which the streaming protocol
+        // (submit right after the query, at most KF_RESULT_SLOTS in flight) cannot guarantee; ship the full rows next time and say so.
+        d->ship_m = d->stride;
+        d->ctx->err = "sfe_kfdb_wait_results: a frame had more matches than the shipped prefix; resubmit (the prefix now covers the capacity)";
+        return SFE_ERR_CAPACITY;
+    }
+    d->ship_m = std::min(d->stride, std::max(d->ship_m, mmax + 64));
+    if (query_ids) *query_ids = sl.qid; if (query_scores) *query_scores = sl.qscore; if (query_n) *query_n = sl.qn;
+    if (pair_kf) *pair_kf = sl.pair_kf; if (best) *best = sl.best; if (matched_n) *matched_n = sl.msub_n; if (n_frames) *n_frames = sl.n;
     return SFE_OK;
 }

@@ -301,6 +301,7 @@ static int create_impl(sfe_context* c)
         sfe_upload_blur_taps(k);
     }
     c->graphs.assign(f.max_pairs + 1, nullptr);
+    c->ship_kp = std::min(P.kp_cap, f.nfeatures + 16); c->ship_m = std::min(P.kp_cap, f.nfeatures + 16);
     if ((size_t)c->sel_cand_cap * 8 > 200 * 1024 || sizeof(int) * ((size_t)f.height + 2 + (size_t)P.kp_cap) > 200 * 1024) {
         c->err = "configuration needs more than 200 KB of shared memory per CTA"; return SFE_ERR_INVALID;
     }
@@ -572,15 +573,56 @@ extern "C" int sfe_get_values(sfe_context* c, int pair, sfe_keypoint* kl, sfe_ke
     return SFE_OK;
 }
 
+// D2H ships CONTENT, not capacity: an image holds ~nfeatures keypoints in `cap` = nfeatures + 64*nlevels slots and a pair
+// far fewer matches.  The asynchronous download copies the first `ship_kp` slots of every image (`ship_m` of every pair)
+// with one strided copy per array -- sizes known on the host before the kernels ran, so nothing waits; sfe_wait_batch
+// fetches the (rare) remainder when a count exceeds what was shipped and raises the sizes for the next batch.
+static int copy_columns(sfe_context* c, void* h, const void* d, size_t elem, int first, int last, int rows)
+{
+    if (last <= first || rows <= 0) return SFE_OK;
+    const size_t pitch = (size_t)c->pack.kp_cap * elem;
+    SFE_CUDA(c, cudaMemcpy2DAsync((uint8_t*)h + (size_t)first * elem, pitch, (const uint8_t*)d + (size_t)first * elem, pitch,
+                                  (size_t)(last - first) * elem, rows, cudaMemcpyDeviceToHost, c->stream));
+    return SFE_OK;
+}
+
 static int enqueue_download(sfe_context* c)
 {
-    const int np = c->last_npairs; const size_t cap = c->pack.kp_cap;
-    SFE_CUDA(c, cudaMemcpyAsync(c->h_kp, c->d_kp, sizeof(sfe_keypoint) * 2 * np * cap, cudaMemcpyDeviceToHost, c->stream));
-    SFE_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc, 32 * 2 * (size_t)np * cap, cudaMemcpyDeviceToHost, c->stream));
-    SFE_CUDA(c, cudaMemcpyAsync(c->h_matches, c->d_matches, sizeof(sfe_dmatch) * np * cap, cudaMemcpyDeviceToHost, c->stream));
+    const int np = c->last_npairs;
+    int r;
+    if ((r = copy_columns(c, c->h_kp, c->d_kp, sizeof(sfe_keypoint), 0, c->ship_kp, 2 * np))) return r;
+    if ((r = copy_columns(c, c->h_desc, c->d_desc, 32, 0, c->ship_kp, 2 * np))) return r;
+    if ((r = copy_columns(c, c->h_matches, c->d_matches, sizeof(sfe_dmatch), 0, c->ship_m, np))) return r;
     SFE_CUDA(c, cudaMemcpyAsync(c->h_kp_count, c->d_kp_count, sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(c, cudaMemcpyAsync(c->h_match_count, c->d_match_count, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, c->stream));
+    c->shipped_kp = c->ship_kp; c->shipped_m = c->ship_m;
+    c->d2h_bytes_last = (size_t)2 * np * c->ship_kp * (sizeof(sfe_keypoint) + 32) + (size_t)np * c->ship_m * sizeof(sfe_dmatch) + (size_t)np * 20;
+    return SFE_OK;
+}
+
+// After the counts have landed: fetch what the speculative copy missed, adapt the shipping sizes.
+static int complete_download(sfe_context* c)
+{
+    const int np = c->last_npairs, cap = c->pack.kp_cap;
+    int kmax = 0, mmax = 0;
+    for (int i = 0; i < 2 * np; ++i) kmax = std::max(kmax, std::min(c->h_kp_count[i], cap));
+    for (int p = 0; p < np; ++p) mmax = std::max(mmax, std::min(c->h_match_count[p], cap));
+    bool more = false; int r;
+    if (kmax > c->shipped_kp) {
+        if ((r = copy_columns(c, c->h_kp, c->d_kp, sizeof(sfe_keypoint), c->shipped_kp, kmax, 2 * np))) return r;
+        if ((r = copy_columns(c, c->h_desc, c->d_desc, 32, c->shipped_kp, kmax, 2 * np))) return r;
+        c->d2h_bytes_last += (size_t)2 * np * (kmax - c->shipped_kp) * (sizeof(sfe_keypoint) + 32);
+        more = true;
+    }
+    if (mmax > c->shipped_m) {
+        if ((r = copy_columns(c, c->h_matches, c->d_matches, sizeof(sfe_dmatch), c->shipped_m, mmax, np))) return r;
+        c->d2h_bytes_last += (size_t)np * (mmax - c->shipped_m) * sizeof(sfe_dmatch);
+        more = true;
+    }
+    if (more) { SFE_CUDA(c, cudaStreamSynchronize(c->stream)); c->d2h_refetches++; }
+    c->ship_kp = std::min(cap, std::max(c->ship_kp, kmax + 16));              // keypoint counts sit at the quota: only ever grows
+    c->ship_m = std::min(cap, std::max(mmax + 64, c->ship_m - (c->ship_m - mmax) / 4));   // matches vary with the scene: follows the recent maximum
     return SFE_OK;
 }
 
@@ -612,6 +654,7 @@ extern "C" int sfe_wait_batch(sfe_context* c, const sfe_keypoint** kps, const ui
     if (!c->have_results) { c->err = "no batch in flight"; return SFE_ERR_STATE; }
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
     fill_counts(c);
+    { const int r = complete_download(c); if (r) return r; }
     if (kps) *kps = c->h_kp; if (desc) *desc = c->h_desc; if (matches) *matches = c->h_matches; if (counts) *counts = c->h_counts;
     c->downloaded = true;
     for (int p = 0; p < c->last_npairs; ++p)
@@ -629,12 +672,12 @@ extern "C" int sfe_download_batch(sfe_context* c, const sfe_keypoint** kps, cons
     SFE_BIND_DEVICE(c);
     if (!c) return SFE_ERR_INVALID;
     if (!c->have_results) { c->err = "no results"; return SFE_ERR_STATE; }
-    const int np = c->last_npairs; const size_t cap = c->pack.kp_cap;
     stage_mark(c, ST_D2H);
-    SFE_CUDA(c, cudaMemcpyAsync(c->h_kp, c->d_kp, sizeof(sfe_keypoint) * 2 * np * cap, cudaMemcpyDeviceToHost, c->stream));
-    SFE_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc, 32 * 2 * (size_t)np * cap, cudaMemcpyDeviceToHost, c->stream));
-    SFE_CUDA(c, cudaMemcpyAsync(c->h_matches, c->d_matches, sizeof(sfe_dmatch) * np * cap, cudaMemcpyDeviceToHost, c->stream));
-    int r = fetch_counts(c); if (r) return r;
+    int r = fetch_counts(c); if (r) return r;                      // synchronous entry: counts first, then exactly the content
+    c->shipped_kp = 0; c->shipped_m = 0; c->d2h_bytes_last = (size_t)c->last_npairs * 20;
+    const int64_t refetches = c->d2h_refetches;
+    r = complete_download(c); if (r) return r;
+    c->d2h_refetches = refetches;                                   // not a mis-speculation: nothing had been shipped yet
     stage_mark(c, ST_COUNT);
     if (kps) *kps = c->h_kp; if (desc) *desc = c->h_desc; if (matches) *matches = c->h_matches; if (counts) *counts = c->h_counts;
     c->downloaded = true;
@@ -837,3 +880,5 @@ extern "C" int sfe_stage_times(sfe_context* c, float* ms, int32_t* launches)
     return SFE_OK;
 }
 extern "C" int64_t sfe_kernel_launches(const sfe_context* c) { return c ? c->launches : 0; }
+extern "C" int64_t sfe_last_d2h_bytes(const sfe_context* c) { return c ? (int64_t)c->d2h_bytes_last : 0; }
+extern "C" int64_t sfe_d2h_refetches(const sfe_context* c) { return c ? c->d2h_refetches : 0; }

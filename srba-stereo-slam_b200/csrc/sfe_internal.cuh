@@ -140,6 +140,8 @@ struct sfe_context {
     int32_t* h_kp_count = nullptr; int32_t* h_match_count = nullptr; int32_t* h_status = nullptr;
     sfe_pair_counts* h_counts = nullptr;
     int last_npairs = 0; bool have_results = false; bool downloaded = false;
+    int ship_kp = 0, ship_m = 0, shipped_kp = 0, shipped_m = 0;   // result slots per image / pair the asynchronous download copies
+    size_t d2h_bytes_last = 0; int64_t d2h_refetches = 0;
     // graph cache, one per batch size
     std::vector<cudaGraphExec_t> graphs;
     // timing

@@ -100,6 +100,15 @@ def load_library():
     L.sfe_kfdb_process_batch.argtypes = [vp, i32]
     L.sfe_kfdb_process_batch_on.argtypes = [vp, vp, i32]
     L.sfe_kfdb_results.argtypes = [vp] + [C.POINTER(vp)] * 6
+    L.sfe_kfdb_submit_results.argtypes = [vp, C.POINTER(i32)]
+    L.sfe_kfdb_wait_results.argtypes = [vp, i32] + [C.POINTER(vp)] * 6 + [C.POINTER(i32)]
+    L.sfe_kfdb_store_pointers.argtypes = [vp, vp]
+    L.sfe_kfdb_set_peers.argtypes = [vp, i32, i32, vp, vp]
+    L.sfe_kfdb_insert_batch_on.argtypes = [vp, vp, i32]
+    L.sfe_kfdb_query_batch_on.argtypes = [vp, vp, i32, i32]
+    L.sfe_last_d2h_bytes.argtypes = [vp]; L.sfe_last_d2h_bytes.restype = C.c_int64
+    L.sfe_d2h_refetches.argtypes = [vp]; L.sfe_d2h_refetches.restype = C.c_int64
+    L.sfe_ipc_export.argtypes = [vp, vp, vp]; L.sfe_ipc_import.argtypes = [vp, vp, C.POINTER(vp)]; L.sfe_ipc_close.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -266,6 +275,8 @@ class StereoFrontEnd:
         self._chk(self.lib.sfe_stage_times(self.h, _p(ms), _p(la)))
         return {self.lib.sfe_stage_name(i).decode(): (float(ms[i]), int(la[i])) for i in range(n)}
     def kernel_launches(self): return int(self.lib.sfe_kernel_launches(self.h))
+    def last_d2h_bytes(self): return int(self.lib.sfe_last_d2h_bytes(self.h))
+    def d2h_refetches(self): return int(self.lib.sfe_d2h_refetches(self.h))
 
 
 class BowDatabase:
@@ -334,12 +345,8 @@ class KeyframeDatabase:
         else:
             src._chk(self.lib.sfe_kfdb_process_batch_on(self.h, src.h, npairs))
 
-    def results(self, npairs):
-        """Returns dict of numpy arrays: query_ids [n,4], query_scores [n,4], query_n [n], pair_kf [n,5],
-        best [n,5,cap] (packed dist<<16 | train index, 0xFFFFFFFF = none), matched_n [n]."""
-        p = [C.c_void_p() for _ in range(6)]
-        self.fe._chk(self.lib.sfe_kfdb_results(self.h, *[C.byref(x) for x in p]))
-        n, cap = npairs, self.fe.kp_cap
+    def _views(self, p, n):
+        cap = self.fe.kp_cap
 
         def view(ptr, dtype, shape):
             cnt = int(np.prod(shape))
@@ -348,3 +355,70 @@ class KeyframeDatabase:
         return {"query_ids": view(p[0], np.int32, (n, 4)), "query_scores": view(p[1], np.float64, (n, 4)),
                 "query_n": view(p[2], np.int32, (n,)), "pair_kf": view(p[3], np.int32, (n, 5)),
                 "best": view(p[4], np.uint32, (n, 5, cap)), "matched_n": view(p[5], np.int32, (n,))}
+
+    def results(self, npairs):
+        """Returns dict of numpy arrays: query_ids [n,4], query_scores [n,4], query_n [n], pair_kf [n,5],
+        best [n,5,cap] (packed dist<<16 | train index, 0xFFFFFFFF = none), matched_n [n]."""
+        p = [C.c_void_p() for _ in range(6)]
+        self.fe._chk(self.lib.sfe_kfdb_results(self.h, *[C.byref(x) for x in p]))
+        return self._views(p, npairs)
+
+    # --- streaming results (pinned slots; `best` rows are only valid up to matched_n) ---
+    def submit_results(self):
+        s = C.c_int32()
+        self.fe._chk(self.lib.sfe_kfdb_submit_results(self.h, C.byref(s)))
+        return s.value
+
+    def wait_results(self, slot, copy=True):
+        p = [C.c_void_p() for _ in range(6)]; n = C.c_int32()
+        self.fe._chk(self.lib.sfe_kfdb_wait_results(self.h, slot, *[C.byref(x) for x in p], C.byref(n)))
+        if not copy:                       # the caller only needs the small arrays (bench): view query_n without copying `best`
+            buf = (C.c_int32 * n.value).from_address(p[2].value)
+            return {"query_n": np.frombuffer(buf, np.int32, n.value), "n": n.value}
+        return self._views(p, n.value)
+
+    # --- two-pass form + one logical database over several ranks ---
+    def insert_batch(self, npairs, src=None):
+        src = src or self.fe
+        src._chk(self.lib.sfe_kfdb_insert_batch_on(self.h, src.h, npairs))
+
+    def query_batch(self, first_local_frame, npairs, src=None):
+        src = src or self.fe
+        src._chk(self.lib.sfe_kfdb_query_batch_on(self.h, src.h, first_local_frame, npairs))
+
+    def store_pointers(self):
+        out = (C.c_void_p * 5)()
+        self.fe._chk(self.lib.sfe_kfdb_store_pointers(self.h, out))
+        return [int(x or 0) for x in out]
+
+    def set_peers(self, rank, starts, ptr_rows):
+        """starts: nranks+1 global shard starts; ptr_rows: nranks rows of 5 device pointers (own row ignored)."""
+        nr = len(ptr_rows)
+        st = np.ascontiguousarray(starts, np.int32); pt = np.ascontiguousarray(np.array(ptr_rows, np.uint64).reshape(nr, 5))
+        self._peer_keep = (st, pt)
+        self.fe._chk(self.lib.sfe_kfdb_set_peers(self.h, nr, rank, _p(st), _p(pt)))
+
+    def connect(self, dist, frames_per_rank):
+        """One logical database over the ranks of `dist` (torch.distributed, one process per GPU): exports this rank's five store
+        arrays with CUDA IPC, maps the peers', tells the kernels.  frames_per_rank: list of shard sizes (global order = rank order)."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = self.store_pointers()
+        handles = []
+        for ptr in mine:
+            h = (C.c_uint8 * 64)()
+            self.fe._chk(self.lib.sfe_ipc_export(self.fe.h, ptr, h)); handles.append(bytes(h))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles)
+        rows = []; self._imports = []
+        for r in range(world):
+            if r == rank:
+                rows.append(mine); continue
+            row = []
+            for hb in gathered[r]:
+                p = C.c_void_p(); hbuf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                self.fe._chk(self.lib.sfe_ipc_import(self.fe.h, hbuf, C.byref(p)))
+                self._imports.append(p.value); row.append(p.value)
+            rows.append(row)
+        starts = np.concatenate([[0], np.cumsum(frames_per_rank)]).astype(np.int32)
+        self.set_peers(rank, starts, rows)
+        return starts

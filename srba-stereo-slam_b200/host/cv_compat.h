@@ -6,7 +6,7 @@
 //   cv::BFMatcher::match        -> the GPU brute-force matcher (sfe_match_bf) through a hook the engine installs
 //                                  (reference call: CSRBAStereoSLAMEstimator.cpp:1447-1452)
 //   cv::findFundamentalMat      -> host/fundamental_ransac.h (reference call: CSRBAStereoSLAMEstimator.cpp:2043)
-// so the reference's data-association functions compile and run unchanged (oracle/ref_build.py does exactly that).
+// so the reference's data-association functions compile and run unchanged (the test-suite compiles them from the reference checkout and does exactly that).
 #pragma once
 #ifdef SRBA_B200_WITH_OPENCV
 #include <opencv2/calib3d/calib3d.hpp>

@@ -1,5 +1,5 @@
 // host_shims.cpp -- C entry points over the host-side data-association code (da_filters.h) for the ctypes test-suite.
-// Same signatures as the shims oracle/ref_build.py puts over the reference's own functions, so one Python driver feeds both
+// Same signatures as the shims the test-suite's reference build puts over the reference's own functions, so one Python driver feeds both
 // with the same keyframes and diffs the results (tests/test_ref_da.py).  No GPU work here: the brute-force result is an input.
 #include <cstring>
 #include <map>

@@ -465,3 +465,58 @@ def test_parameter_sweep(mods, w, h, nlevels, scale, nfeat, fth, eth, bm, pm):
             assert np.array_equal(m[f], om[f]), f
     finally:
         fe.close()
+
+
+def test_fast_score_ties_beyond_the_candidate_list_are_cut_deterministically():
+    """A binary checkerboard makes every corner score the same: the ties at the retainBest(2q) cut exceed the shared candidate list.
+    That used to fail the frame with SFE_ERR_CAPACITY after an order-dependent truncation; now the ties with the smallest (y, x) are
+    kept (documented deviation: OpenCV would carry all of them into the Harris stage), the frame succeeds and is reproducible."""
+    from srba_stereo_slam_b200 import frontend
+    W, H = 1241, 376
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = (((yy // 6) + (xx // 6)) % 2 * 200 + 20).astype(np.uint8)
+    fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=1, nfeatures=300, max_pairs=1)
+    try:
+        outs = []
+        for _ in range(3):
+            fe.process_stereo(img, img)                          # must not raise SfeError(CAPACITY)
+            kl, kr, dl, dr, m = fe.get_values(0)
+            outs.append((kl.copy(), dl.copy(), m.copy()))
+        n_raw = len(fe.get_raw_corners(0, 0)[0])
+        assert n_raw > 2 * 300 + 1024                            # far more equal-score corners than the list holds
+        assert len(outs[0][0]) >= 300
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
+        assert np.array_equal(outs[0][0], fe.get_values(0)[1])    # left == right image -> identical keypoints
+    finally:
+        fe.close()
+
+
+def test_match_bf_batch_device_initialises_its_keys_and_empty_train_sets():
+    """sfe_match_bf_batch_device resets the packed keys itself (the header promises 0xFFFFFFFF for an empty train set; the kernel
+    merges its train splits with atomicMin): a poisoned output buffer must not leak through."""
+    import ctypes as C
+    import torch
+    from srba_stereo_slam_b200 import frontend
+    from oracle import oracle as orc
+    rng = np.random.default_rng(2)
+    nq = [40, 17, 33]; nt = [50, 0, 21]
+    Q = rng.integers(0, 256, (sum(nq), 32), dtype=np.uint8); T = rng.integers(0, 256, (sum(nt), 32), dtype=np.uint8)
+    fe = frontend.StereoFrontEnd(width=320, height=240, nlevels=1, nfeatures=100, max_pairs=1)
+    try:
+        dev = torch.device("cuda", 0)
+        dq = torch.from_numpy(Q).to(dev); dt = torch.from_numpy(T).to(dev)
+        qo = torch.tensor(np.concatenate([[0], np.cumsum(nq)]), dtype=torch.int32, device=dev)
+        to = torch.tensor(np.concatenate([[0], np.cumsum(nt)]), dtype=torch.int32, device=dev)
+        best = torch.full((sum(nq),), 12345, dtype=torch.int32, device=dev)          # poison
+        torch.cuda.synchronize()
+        vp = C.c_void_p
+        fe._chk(fe.lib.sfe_match_bf_batch_device(fe.h, vp(dq.data_ptr()), vp(qo.data_ptr()), vp(dt.data_ptr()), vp(to.data_ptr()), 3, max(nq), vp(best.data_ptr())))
+        fe.synchronize()
+        b = best.cpu().numpy().view(np.uint32)
+        o0 = orc.match_bf(Q[:40], T[:50]); o2 = orc.match_bf(Q[57:], T[50:])
+        assert np.array_equal(b[:40], (o0["distance"].astype(np.uint32) << 16) | o0["trainIdx"].astype(np.uint32))
+        assert np.all(b[40:57] == 0xFFFFFFFF)
+        assert np.array_equal(b[57:], (o2["distance"].astype(np.uint32) << 16) | o2["trainIdx"].astype(np.uint32))
+    finally:
+        fe.close()
