@@ -219,6 +219,12 @@ class StereoFrontEnd:
         self._chk(self.lib.sfe_synchronize(self.h))
         return npairs
 
+    def upload_async(self, npairs):
+        """H2D of the context's own pinned staging buffer, no synchronisation (link probes)."""
+        n = C.c_size_t()
+        p = self.lib.sfe_host_staging(self.h, C.byref(n))
+        self._chk(self.lib.sfe_upload_batch(self.h, p, npairs, self.cfg.width, self.cfg.width * self.cfg.height))
+
     def process_device(self, npairs):
         self._chk(self.lib.sfe_process_batch_device(self.h, npairs))
 
