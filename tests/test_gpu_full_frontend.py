@@ -87,7 +87,7 @@ def _check_frame(got, exp, tag):
     assert got["query_scores"][:len(exp["res"])].tolist() == [r_[1] for r_ in exp["res"]], tag
     assert got["pair_kf"].tolist() == exp["kf"], tag
     for slot, k in enumerate(exp["kf"]):
-        if k is None or exp["keys"][slot] is None:
+        if k is None or exp["keys"][slot] is None or (len(exp["keys"][slot]) == 0 and n > 0):      # no keyframe in the slot / it has no stereo matches
             assert np.all(got["best"][slot][:max(n, 1)] == 0xFFFFFFFF), (tag, slot)
         else:
             assert np.array_equal(got["best"][slot][:n], exp["keys"][slot]), (tag, slot)
@@ -103,8 +103,9 @@ def test_one_logical_database_over_ranks_equals_single_rank(voc):
     W, H, NL, NFEAT, B = 640, 192, 4, 300, 4
     shards = [8, 5, 7]                                    # ragged on purpose
     NF = sum(shards)
-    sc = synth.CorridorScene(seed=8, width=W, height=H, loop_radius=1.7)     # tight ring: the camera revisits places within 20 frames
-    frames = sc.sequence(NF)
+    seq = synth.CorridorScene(seed=8, width=W, height=H).sequence(8)
+    frames = np.concatenate([seq[0:8], seq[3:8], seq[0:7]])                  # ranks 1 and 2 REVISIT places rank 0 owns: cross-shard loop closures
+    assert len(frames) == NF
     exp = _oracle_frontend(voc, frames, NFEAT, NL)
     # ---- single rank, streaming (insert + query per batch) ----
     fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=NL, nfeatures=NFEAT, max_pairs=B)
