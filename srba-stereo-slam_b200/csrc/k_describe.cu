@@ -206,8 +206,238 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused variant (SFE_BLUR_CV24_FIXED, edge_threshold >= 22): the 7x7 Gaussian is evaluated INSIDE this kernel, on the one
+// unblurred 43x43 patch a keypoint needs, instead of blurring every pyramid level into a second arena first.  The
+// OpenCV-2.4 fixed-point blur has no intermediate rounding (row sums <= 255*257 fit 16 bits, one (s + 2^15) >> 16 at the
+// end), so the separable pass over the patch gives bit for bit the bytes the whole-image blur would give at those
+// positions.  What it removes: blur_kernel (read P + write P per image), the blurred arena (half the context's
+// footprint), the second patch staging (43 rows instead of 31 + 37).  Per warp:
+//   stage   rows y-21..y+21 of the 8-byte aligned span that holds columns x-21..x+21 (7 cp.async of 8 bytes per row)
+//   orient  intensity centroid on rows y-15..y+15 of the same patch (as above)
+//   rows    7-tap row pass, two rows x four outputs per work item: DP4A on the ALIGNED words with shifted tap patterns,
+//           the sums of rows 2p and 2p+1 packed into one word (k_blur.cu's formulation)
+//   cols    7-tap column pass: lane = (4-column group, block of 12/13 rows) sliding down its rows with a window of four
+//           packed row pairs, 4 DP2A per output, saturate, pack -> the 37x40 blurred patch overwrites the raw one
+//   tests   as above, on the blurred patch.
+// ------------------------------------------------------------------------------------------------------------------------
+#define FZ_R 21                          // raw patch radius: 18 (sampler reach) + 3 (blur)
+#define FZ_ROWS 44                       // 43 rows + one spare (the last row pair is (42, 43))
+#define FZ_PITCH 88                      // bytes: 8 pad | 56 data | 24 pad; 22 words: consecutive row PAIRS land 12 banks apart (row pass: lanes span 4 pairs x 10 groups)
+#define FZ_PAIRS 22
+#define FZ_KPW 4                         // keypoint slots a warp describes in turn
+#define FZ_WARPS 6                       // 6 x 7.2 KB of patch buffers per CTA: five CTAs (30 warps) per SM
+#define FZ_GROUPS 10                     // 4-column output groups covering x-18 .. x+18 for every alignment
+#define FZ_RB_PITCH (FZ_GROUPS * 4)      // row-sum words per row pair
+#define FZ_WARP_BYTES (FZ_ROWS * FZ_PITCH + FZ_PAIRS * FZ_RB_PITCH * 4)
+
+__global__ void __launch_bounds__(FZ_WARPS * 32, 5)
+describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr,
+                      const uint32_t* __restrict__ sel_xy, const float* __restrict__ sel_resp,
+                      const int32_t* __restrict__ sel_count,
+                      sfe_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ kp_count)
+{
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    __shared__ uint32_t pat_s[256];
+    __shared__ uint32_t disc_mask[16 * 9];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int img = blockIdx.y;
+    for (int t = tid; t < 256; t += FZ_WARPS * 32) pat_s[t] = reinterpret_cast<const uint32_t*>(d_brief_pattern)[8 * (t & 31) + (t >> 5)];
+    if (tid < 128) {
+        const int av = tid >> 3, k = tid & 7, m = c_umax[av];
+        uint32_t mk = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (abs(4 * k + b - 15) <= m) mk |= 0xffu << (8 * b);
+        disc_mask[av * 9 + k] = mk;
+    }
+    __syncthreads();
+
+    // slot -> (level, index): lanes 0..7 hold the per-level counts, an 8-lane scan gives the level boundaries (once per warp)
+    const int cnt = lane < P.nlevels ? sel_count[(size_t)img * P.nlevels + lane] : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (blockIdx.x == 0 && tid == 7) kp_count[img] = inc;
+    // a warp describes FZ_KPW keypoint slots in turn: the per-CTA set-up (pattern table, disc masks) is paid once per 6 x FZ_KPW keypoints
+#pragma unroll 1
+    for (int kk = 0; kk < FZ_KPW; ++kk) {
+    const int slot = (blockIdx.x * FZ_KPW + kk) * FZ_WARPS + warp;
+    const uint32_t below = __ballot_sync(0xffffffffu, lane < P.nlevels && slot < inc);
+    if (below == 0u) break;                                                      // warp-uniform; later slots are empty too
+    const int level = __ffs(below) - 1;
+    const int idx = slot - (__shfl_sync(0xffffffffu, inc, level) - __shfl_sync(0xffffffffu, cnt, level));
+
+    const LevelGeom& g = P.g[level];
+    const size_t so = (size_t)img * P.sel_img_stride + g.sel_ofs + idx;
+    const uint32_t xy = sel_xy[so];
+    const int x = xy & 0xffff, y = xy >> 16;
+    const size_t lofs = g.lvl_ofs + (size_t)img * g.img_bytes;
+    const int pitch = g.pitch;
+
+    uint8_t* raw = fz_smem + (size_t)warp * FZ_WARP_BYTES;                       // [FZ_ROWS][FZ_PITCH], data at byte 8 of a row
+    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(raw + FZ_ROWS * FZ_PITCH);    // [FZ_PAIRS][FZ_RB_PITCH]
+    const int xb = (x - FZ_R) & ~7, bsh = (x - FZ_R) - xb;                       // data byte c of a row <-> image column xb + c
+    // ---- stage the raw patch: lane = (row of a group of four, 8-byte piece); 11 steps of 4 rows, immediate offsets only -----------
+    {
+        const int part = lane & 7, rsub = lane >> 3;                             // piece 7 does not exist: those lanes idle
+        const uint8_t* src = pyr + lofs + (size_t)(y - FZ_R + rsub) * pitch + xb + 8 * part;
+        uint8_t* dst = raw + rsub * FZ_PITCH + 8 + 8 * part;
+        const size_t step = (size_t)4 * pitch;
+        if (part < 7) {
+#pragma unroll
+            for (int k = 0; k < FZ_ROWS / 4; ++k) { cp_async8(dst + 4 * k * FZ_PITCH, src); src += step; }     // rows 0 .. 43 (row 43 only feeds zero-weight taps)
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- orientation on rows y-15 .. y+15, columns x-15 .. x+15 of the raw patch --------------------------------------------
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - 15;
+        const int ob = 8 + bsh + (FZ_R - 15);                                    // byte of column x-15 in a row
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + (lane + FZ_R - 15) * FZ_PITCH) + (ob >> 2);
+        const uint32_t* mk = disc_mask + abs(v) * 9;
+        const int bs = (ob & 3) * 8;
+        uint32_t w[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = rw[k];
+        int s1 = 0, su = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t a = __funnelshift_r(w[k], w[k + 1], bs) & mk[k];
+            s1 = (int)__dp4a(a, 0x01010101u, (uint32_t)s1);
+            su = dp4a_u8_s8(a, orient_wu(k), su);
+        }
+        m10 = su; m01 = v * s1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = cv_fast_atan2((float)m01, (float)m10);
+
+    // ---- blur, row pass: item = (row pair, 4-column group) ---------------------------------------------------------------------
+    const int g0 = (bsh + 3) >> 2;                                               // first group that holds column x-18
+    {
+        auto row4 = [](uint32_t A, uint32_t B, uint32_t C, uint32_t (&o)[4]) {    // A|B|C = pixels x-4..x-1 | x..x+3 | x+4..x+7
+            o[0] = __dp4a(B, 0x12223137u, __dp4a(A, 0x31221200u, 0u));
+            o[1] = __dp4a(C, 0x00000012u, __dp4a(B, 0x22313731u, __dp4a(A, 0x22120000u, 0u)));
+            o[2] = __dp4a(C, 0x00001222u, __dp4a(B, 0x31373122u, __dp4a(A, 0x12000000u, 0u)));
+            o[3] = __dp4a(C, 0x00122231u, __dp4a(B, 0x37312212u, 0u));
+        };
+        // lane = (group gq of 10, row pair of three): 8 steps of three row pairs, immediate offsets, no index arithmetic; the three
+        // pairs of a step sit 12 banks apart (FZ_PITCH), so the 30 active lanes read conflict-free
+        const int prl = lane / FZ_GROUPS, gq = lane - prl * FZ_GROUPS;
+        const uint32_t* c = reinterpret_cast<const uint32_t*>(raw) + 2 + g0 + 2 * prl * (FZ_PITCH / 4) + gq;   // data starts at word 2 of a row
+        uint32_t* ob = rowbuf + prl * FZ_RB_PITCH + 4 * gq;
+        if (lane < 3 * FZ_GROUPS) {
+#pragma unroll
+            for (int it = 0; it < (FZ_PAIRS + 2) / 3; ++it) {
+                if (3 * it + 2 >= FZ_PAIRS && 3 * it + prl >= FZ_PAIRS) break;   // last step: only pair 21 exists
+                const uint32_t* cc = c + 6 * it * (FZ_PITCH / 4);
+                uint32_t lo[4], hi[4];
+                row4(cc[-1], cc[0], cc[1], lo);
+                row4(cc[FZ_PITCH / 4 - 1], cc[FZ_PITCH / 4], cc[FZ_PITCH / 4 + 1], hi);
+                *reinterpret_cast<uint4*>(ob + 3 * it * FZ_RB_PITCH) =
+                    make_uint4(__byte_perm(lo[0], hi[0], 0x5410), __byte_perm(lo[1], hi[1], 0x5410),
+                               __byte_perm(lo[2], hi[2], 0x5410), __byte_perm(lo[3], hi[3], 0x5410));
+            }
+        }
+    }
+    __syncwarp();
+    // ---- blur, column pass: lane = (group, row block); output row yy <-> image row y-18+yy reads raw rows yy .. yy+6 -------------------
+    uint8_t* bp = raw;                                                           // the blurred patch [37][BP_PITCH] overwrites the raw one
+    if (lane < 3 * FZ_GROUPS) {
+        const int rb = lane / FZ_GROUPS, gq = lane - rb * FZ_GROUPS;
+        const int r0 = 12 * rb;                                                  // row blocks [0,12) [12,24) [24,37): even starts
+        auto col = [](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, bool odd) -> uint32_t {
+            uint32_t s = odd ? __dp2a_lo(w3, 0x1222u, __dp2a_lo(w2, 0x3137u, __dp2a_lo(w1, 0x3122u, __dp2a_lo(w0, 0x1200u, 1u << 15))))
+                             : __dp2a_lo(w3, 0x0012u, __dp2a_lo(w2, 0x2231u, __dp2a_lo(w1, 0x3731u, __dp2a_lo(w0, 0x2212u, 1u << 15))));
+            return min(s, 0x00ffffffu);
+        };
+        const uint4* rp = reinterpret_cast<const uint4*>(rowbuf + 4 * gq) + (r0 >> 1) * (FZ_RB_PITCH / 4);
+        uint32_t* outp = reinterpret_cast<uint32_t*>(bp + r0 * BP_PITCH + 4 * gq);
+        uint4 W[10];                                                             // row pairs j0 .. j0+9: 7 steps x 2 rows, fully unrolled (no window moves)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) W[k] = rp[k * (FZ_RB_PITCH / 4)];
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {
+            if (it < 6 || rb == 2) W[it + 3] = rp[(it + 3) * (FZ_RB_PITCH / 4)];   // the 7th step only exists for the 13-row block
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int yy = 2 * it + o;                                       // row within the block
+                if (yy >= 12 && (rb != 2 || yy > 12)) continue;
+                const uint32_t s0 = col(W[it].x, W[it + 1].x, W[it + 2].x, W[it + 3].x, o), s1 = col(W[it].y, W[it + 1].y, W[it + 2].y, W[it + 3].y, o);
+                const uint32_t s2 = col(W[it].z, W[it + 1].z, W[it + 2].z, W[it + 3].z, o), s3 = col(W[it].w, W[it + 1].w, W[it + 2].w, W[it + 3].w, o);
+                outp[yy * (BP_PITCH / 4)] = __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);   // nobody reads the raw patch any more
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- 256 tests, 8 per lane, on the blurred patch: byte (yy, 4*gq + e) <-> pixel (xb + 4*(g0 + gq) + e, y - 18 + yy) ---------------
+    const float arad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+    double dsa, dca; sincos((double)arad, &dsa, &dca);                           // one range reduction for both (same values as sin / cos)
+    const float ca = (float)dca, sa = (float)dsa;
+    const float MAGIC = 12582912.f;
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(bp) + PATCH_R * BP_PITCH + (bsh + FZ_R - 4 * g0) - 0x4B400000u * (BP_PITCH + 1u);
+    uint32_t byte = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = pat_s[j * 32 + lane];
+        const float ax = (float)(int8_t)(e & 0xff), ay = (float)(int8_t)((e >> 8) & 0xff);
+        const float bx = (float)(int8_t)((e >> 16) & 0xff), by = (float)(int8_t)(e >> 24);
+        const float fx0 = __fadd_rn(__fsub_rn(__fmul_rn(ax, ca), __fmul_rn(ay, sa)), MAGIC);
+        const float fy0 = __fadd_rn(__fadd_rn(__fmul_rn(ax, sa), __fmul_rn(ay, ca)), MAGIC);
+        const float fx1 = __fadd_rn(__fsub_rn(__fmul_rn(bx, ca), __fmul_rn(by, sa)), MAGIC);
+        const float fy1 = __fadd_rn(__fadd_rn(__fmul_rn(bx, sa), __fmul_rn(by, ca)), MAGIC);
+        const uint32_t t0 = lds_u8(__float_as_uint(fy0) * BP_PITCH + __float_as_uint(fx0) + cbase);
+        const uint32_t t1 = lds_u8(__float_as_uint(fy1) * BP_PITCH + __float_as_uint(fx1) + cbase);
+        byte |= (uint32_t)(t0 < t1) << j;
+    }
+    uint32_t wv = byte << (8 * (lane & 3));
+    wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
+    wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
+    const size_t ko = (size_t)img * P.kp_cap + slot;
+    if ((lane & 3) == 0) reinterpret_cast<uint32_t*>(desc + ko * 32)[lane >> 2] = wv;
+
+    if (lane == 0) {
+        sfe_keypoint k;
+        k.x = (float)x; k.y = (float)y;
+        if (level != 0) { k.x = __fmul_rn(k.x, g.scale); k.y = __fmul_rn(k.y, g.scale); }
+        k.size = __fmul_rn(31.f, g.scale);
+        k.angle = angle;
+        k.response = sel_resp[so];
+        k.octave = level; k.class_id = -1;
+        kps[ko] = k;
+    }
+    __syncwarp();                                                                // the next keypoint's staging overwrites the patch buffers
+    }
+}
+
+bool describe_is_fused(const sfe_context* c)
+{
+    return c->cfg.blur_mode == SFE_BLUR_CV24_FIXED && c->cfg.edge_threshold >= FZ_R + 1 && !c->force_unfused;
+}
+
+void prepare_describe(sfe_context* c)
+{
+    sfe_raise_dynamic_smem((const void*)describe_fused_kernel, c->cfg.device, FZ_WARPS * FZ_WARP_BYTES);
+}
+
+static_assert(FZ_ROWS * FZ_PITCH >= BP_ROWS * BP_PITCH, "the blurred patch must fit over the raw one");
 void launch_describe(sfe_context* c, int nimg)
 {
+    if (describe_is_fused(c)) {
+        dim3 grid((c->pack.kp_cap + FZ_WARPS * FZ_KPW - 1) / (FZ_WARPS * FZ_KPW), nimg);
+        describe_fused_kernel<<<grid, FZ_WARPS * 32, FZ_WARPS * FZ_WARP_BYTES, c->stream>>>(c->pack, c->d_pyr, c->d_sel_xy, c->d_sel_resp,
+                                                                                              c->d_sel_count, c->d_kp, c->d_desc, c->d_kp_count);
+        c->launches++;
+        return;
+    }
     dim3 grid((c->pack.kp_cap + DESC_WARPS - 1) / DESC_WARPS, nimg);
     describe_kernel<<<grid, DESC_WARPS * 32, 0, c->stream>>>(c->pack, c->d_pyr, c->d_blur, c->d_sel_xy, c->d_sel_resp,
                                                              c->d_sel_count, c->d_kp, c->d_desc, c->d_kp_count);

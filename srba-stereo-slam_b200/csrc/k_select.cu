@@ -210,21 +210,57 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     float* out_r = sel_resp + (size_t)img * P.sel_img_stride + g.sel_ofs;
     __shared__ uint32_t skey[SEL_SORT_CAP];
     __shared__ float sval[SEL_SORT_CAP];
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    for (int base = 0; base < nc; base += SEL_THREADS) {          // warp-aggregated compaction of the kept points
-        const int i = base + tid;
-        const bool kp = i < nc && cand_resp[i] >= boundary;
-        const uint32_t bal = __ballot_sync(0xffffffffu, kp);
-        if (bal) {
-            int wb = 0;
-            if (lane == 0) wb = atomicAdd(&s_n, __popc(bal));
-            wb = __shfl_sync(0xffffffffu, wb, 0);
-            const int slot = wb + __popc(bal & ((1u << lane) - 1u));
-            if (kp && slot < SEL_SORT_CAP) { skey[slot] = cand_xy[i]; sval[slot] = cand_resp[i]; }
+    // Ties at the Harris cut that do not fit the selection list (identical structures repeated over the image: every response equal):
+    // as at the FAST-score cut above, the ties with the smallest (y, x) are kept -- deterministic, and the frame succeeds.
+    uint32_t harris_tie_max = 0xffffffffu;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        for (int base = 0; base < nc; base += SEL_THREADS) {      // warp-aggregated compaction of the kept points
+            const int i = base + tid;
+            const bool kp = i < nc && (cand_resp[i] > boundary || (cand_resp[i] == boundary && cand_xy[i] <= harris_tie_max));
+            const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+            if (bal) {
+                int wb = 0;
+                if (lane == 0) wb = atomicAdd(&s_n, __popc(bal));
+                wb = __shfl_sync(0xffffffffu, wb, 0);
+                const int slot = wb + __popc(bal & ((1u << lane) - 1u));
+                if (kp && slot < SEL_SORT_CAP) { skey[slot] = cand_xy[i]; sval[slot] = cand_resp[i]; }
+            }
         }
+        __syncthreads();
+        if (s_n <= g.sel_cap || attempt == 1) break;               // uniform
+        // overflow: need = sel_cap - #(response > boundary) ties; 4-pass radix select of the need-th smallest (y<<16|x) among the ties
+        if (tid == 0) { s_k = 0; s_prefix = 0u; }
+        __syncthreads();
+        int above = 0;
+        for (int i = tid; i < nc; i += SEL_THREADS) above += cand_resp[i] > boundary;
+        if (above) atomicAdd(&s_k, above);
+        __syncthreads();
+        const int need = max(g.sel_cap - s_k, 1);
+        __syncthreads();
+        if (tid == 0) s_k = need;
+        uint32_t mask = 0u;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int i = tid; i < nc; i += SEL_THREADS) {
+                const uint32_t k = ~cand_xy[i];                   // inverted: the k-th from the top = the k-th smallest position
+                if (cand_resp[i] == boundary && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int b, ab;
+                kth_from_top(hist, s_k, lane, b, ab);
+                __syncwarp();
+                if (lane == 0) { s_k = s_k - ab; s_prefix = prefix | ((uint32_t)b << shift); }
+            }
+            mask |= 255u << shift;
+            __syncthreads();
+        }
+        harris_tie_max = ~s_prefix;
     }
-    __syncthreads();
     const int nk_all = s_n;
     if (nk_all <= SEL_SORT_CAP) {
         int np2 = 1; while (np2 < nk_all) np2 <<= 1;
@@ -246,10 +282,10 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     } else {
         // very large quotas: rank by counting (O(n^2), exact)
         for (int i = tid; i < nc; i += SEL_THREADS) {
-            if (!(cand_resp[i] >= boundary)) continue;
             const uint32_t key = cand_xy[i];
+            if (!(cand_resp[i] > boundary || (cand_resp[i] == boundary && key <= harris_tie_max))) continue;
             int rank = 0;
-            for (int j = 0; j < nc; ++j) rank += (cand_resp[j] >= boundary) && (cand_xy[j] < key);
+            for (int j = 0; j < nc; ++j) rank += (cand_resp[j] > boundary || (cand_resp[j] == boundary && cand_xy[j] <= harris_tie_max)) && (cand_xy[j] < key);
             if (rank < g.sel_cap) { out_xy[rank] = key; out_r[rank] = cand_resp[i]; }
         }
     }

@@ -5,6 +5,7 @@
 // headers for the reference call sites (EST.cpp:112,267,1135-1142).
 #include "sfe_internal.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cfloat>
 #include <cstring>
 #include <algorithm>
@@ -184,9 +185,12 @@ static int create_impl(sfe_context* c)
     // ---- device memory ------------------------------------------------------------------------
     const int NI = c->NI;
     SFE_CUDA(c, dalloc(&c->d_pyr, arena));
-    SFE_CUDA(c, dalloc(&c->d_blur, arena));
     SFE_CUDA(c, cudaMemset(c->d_pyr, 0, arena));
-    SFE_CUDA(c, cudaMemset(c->d_blur, 0, arena));
+    c->force_unfused = getenv("SFE_FORCE_UNFUSED_BLUR") != nullptr;
+    if (!describe_is_fused(c)) {           // the blurred arena only exists where a separate blur kernel runs (float mode, edge_threshold < 22)
+        SFE_CUDA(c, dalloc(&c->d_blur, arena));
+        SFE_CUDA(c, cudaMemset(c->d_blur, 0, arena));
+    }
     SFE_CUDA(c, dalloc(&c->d_raw, (size_t)NI * P.raw_img_stride));
     SFE_CUDA(c, dalloc(&c->d_raw_count, (size_t)NI * L));
     SFE_CUDA(c, dalloc(&c->d_sel_xy, (size_t)NI * P.sel_img_stride));
@@ -307,6 +311,7 @@ static int create_impl(sfe_context* c)
     }
     prepare_select(c);
     prepare_rowband(c);
+    prepare_describe(c);
     SFE_CUDA(c, cudaGetLastError());
     SFE_CUDA(c, cudaDeviceSynchronize());
     return SFE_OK;
@@ -384,7 +389,7 @@ static void enqueue_kernels(sfe_context* c, int npairs)
     stage_mark(c, ST_SELECT);
     launch_select(c, nimg);
     stage_mark(c, ST_BLUR);
-    launch_blur(c, nimg);
+    if (!describe_is_fused(c)) launch_blur(c, nimg);
     stage_mark(c, ST_DESCRIBE);
     launch_describe(c, nimg);
     stage_mark(c, ST_MATCH_LR);
@@ -689,6 +694,13 @@ extern "C" int sfe_get_level(sfe_context* c, int img, int level, int blurred, ui
     SFE_BIND_DEVICE(c);
     if (!c || !out || level < 0 || level >= c->pack.nlevels || img < 0 || img >= c->NI) return SFE_ERR_INVALID;
     const LevelGeom& g = c->pack.g[level];
+    if (blurred && describe_is_fused(c)) {
+        // debug / parity tap: the hot path never materialises the blurred levels in this mode -- blur them now, once, on demand
+        if (!c->have_results) { c->err = "no results: call a process function first"; return SFE_ERR_STATE; }
+        if (!c->d_blur) { SFE_CUDA(c, dalloc(&c->d_blur, c->arena_bytes)); SFE_CUDA(c, cudaMemsetAsync(c->d_blur, 0, c->arena_bytes, c->stream)); }
+        launch_blur(c, 2 * c->last_npairs);
+        SFE_CUDA(c, cudaGetLastError());
+    }
     const uint8_t* base = (blurred ? c->d_blur : c->d_pyr) + g.lvl_ofs + (size_t)img * g.img_bytes;
     SFE_CUDA(c, cudaMemcpy2DAsync(out, g.w, base, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost, c->stream));
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -870,7 +882,7 @@ extern "C" int sfe_stage_times(sfe_context* c, float* ms, int32_t* launches)
     if (!c || !ms) return SFE_ERR_INVALID;
     SFE_CUDA(c, cudaStreamSynchronize(c->stream));
     const int L = c->pack.nlevels;
-    const int nl[ST_COUNT] = { 0, L - 1, 1, 1, 1, 1, 2, 0 };
+    const int nl[ST_COUNT] = { 0, L - 1, 1, 1, describe_is_fused(c) ? 0 : 1, 1, 2, 0 };
     for (int s = 0; s < ST_COUNT; ++s) {
         ms[s] = 0.f;
         if (s == ST_H2D || s == ST_D2H) { if (cudaEventElapsedTime(&ms[s], c->ev_stage[s], c->ev_stage[s + 1]) != cudaSuccess) { ms[s] = 0.f; cudaGetLastError(); } }

@@ -115,6 +115,7 @@ struct sfe_context {
     int4* d_btile_tab = nullptr;             // blur tile -> {level, x0, y0, 0}   // per 4 destination columns: {src base, PRMT selectors, 4 coefficient pairs}
     CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 176x48-box maps over the same levels, source side of the pyramid kernel
     int NI = 0;                              // images the arenas are sized for (2*max_pairs)
+    bool force_unfused = false;              // debugging / A-B timing: keep the separate blur kernel even where the fused describe applies
     int sel_cand_cap = 0;                    // select kernel: shared candidate list capacity
     bool select_attr_set = false;
     uint8_t* d_pyr = nullptr;                // pyramid arena
@@ -191,6 +192,8 @@ void prepare_select(sfe_context* c);
 void prepare_rowband(sfe_context* c);
 void launch_blur(sfe_context* c, int nimg);
 void launch_describe(sfe_context* c, int nimg);
+bool describe_is_fused(const sfe_context* c);   // the 7x7 blur is evaluated inside the describe kernel (no blur launch, no blurred arena)
+void prepare_describe(sfe_context* c);
 void launch_match_rowband(sfe_context* c, int npairs);
 void launch_unpack(sfe_context* c, int nimg);
 void launch_match_bf(cudaStream_t s, const uint8_t* d_query, const int32_t* d_q_ofs, const uint8_t* d_train,

@@ -468,13 +468,13 @@ def test_parameter_sweep(mods, w, h, nlevels, scale, nfeat, fth, eth, bm, pm):
 
 
 def test_fast_score_ties_beyond_the_candidate_list_are_cut_deterministically():
-    """A binary checkerboard makes every corner score the same: the ties at the retainBest(2q) cut exceed the shared candidate list.
+    """A lattice of identical bright dots makes every corner score the same: the ties at the retainBest(2q) cut exceed the shared candidate list.
     That used to fail the frame with SFE_ERR_CAPACITY after an order-dependent truncation; now the ties with the smallest (y, x) are
     kept (documented deviation: OpenCV would carry all of them into the Harris stage), the frame succeeds and is reproducible."""
     from srba_stereo_slam_b200 import frontend
     W, H = 1241, 376
     yy, xx = np.mgrid[0:H, 0:W]
-    img = (((yy // 6) + (xx // 6)) % 2 * 200 + 20).astype(np.uint8)
+    img = np.where(((yy % 8) == 4) & ((xx % 8) == 4), 220, 20).astype(np.uint8)        # single bright pixels on an 8-px lattice: ~7000 corners of score 199
     fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=1, nfeatures=300, max_pairs=1)
     try:
         outs = []
