@@ -381,7 +381,6 @@ def main():
         db1 = kfdb.size()
         # parity of the last timed batch (keyframes db1-B .. db1-1) against the sequential oracle.  All batches hold the same B pairs
         # (64 distinct), so entry e of the database is pair (e % B) % 64.
-        res_last = kfdb.results(B)
         ndist = min(B, 64)
         ovec = {}; osub = {}
 
@@ -390,27 +389,31 @@ def main():
                 ol, odl, orr, odr, om = oracle_pair(k)
                 w_, wt_ = orc.bow_transform(voc, odl); ovec[k] = orc.bow_vector(voc, w_, wt_); osub[k] = odl[om["queryIdx"]]
             return ovec[k]
-        for q in sorted(int(x) for x in rng_p.choice(B, size=min(K_PAR, B), replace=False)):
-            g = db1 - B + q
-            qw, qv = o_vec(q % ndist)
-            sc_d = {}
-            for k in range(ndist):
-                dw, dv = o_vec(k); s_, common = orc.bow_l1_raw(qw, qv, dw, dv); sc_d[k] = (s_, common)
-            ent = [(sc_d[(e % B) % ndist][0], e) for e in range(g) if sc_d[(e % B) % ndist][1]]
-            ent.sort(); top = [(e, -s_ / 2.0) for s_, e in ent[:4]]
-            ok = int(res_last["query_n"][q]) == len(top) and res_last["query_ids"][q][:len(top)].tolist() == [t[0] for t in top] \
-                and res_last["query_scores"][q][:len(top)].tolist() == [t[1] for t in top]
-            check("full frame %d BoW top-4" % g, ok)
-            exp_kf = [g - 1] + [(t[0] if t[0] != g - 1 else -1) for t in top] + [-1] * (4 - len(top))
-            okm = res_last["pair_kf"][q].tolist() == exp_kf
-            cur = osub[q % ndist]
-            for slot, kf in enumerate(exp_kf):
-                if kf < 0 or not okm:
-                    continue
-                o_vec((kf % B) % ndist)
-                obf = orc.match_bf(cur, osub[(kf % B) % ndist])
-                okm = okm and np.array_equal(res_last["best"][q][slot][:len(cur)], (obf["distance"].astype(np.uint32) << 16) | obf["trainIdx"].astype(np.uint32))
-            check("full frame %d association keys" % g, okm)
+
+        def check_full_batch(res, first_id, tag):
+            """res: results of a batch whose frame q has global keyframe id first_id + q; every database entry e holds pair (e % B) % 64."""
+            for q in sorted(int(x) for x in rng_p.choice(B, size=min(K_PAR, B), replace=False)):
+                g = first_id + q
+                qw, qv = o_vec(q % ndist)
+                sc_d = {}
+                for k in range(ndist):
+                    dw, dv = o_vec(k); s_, common = orc.bow_l1_raw(qw, qv, dw, dv); sc_d[k] = (s_, common)
+                ent = [(sc_d[(e % B) % ndist][0], e) for e in range(g) if sc_d[(e % B) % ndist][1]]
+                ent.sort(); top = [(e, -s_ / 2.0) for s_, e in ent[:4]]
+                ok = int(res["query_n"][q]) == len(top) and res["query_ids"][q][:len(top)].tolist() == [t[0] for t in top] \
+                    and res["query_scores"][q][:len(top)].tolist() == [t[1] for t in top]
+                check("%s frame %d BoW top-4" % (tag, g), ok)
+                exp_kf = [g - 1] + [(t[0] if t[0] != g - 1 else -1) for t in top] + [-1] * (4 - len(top))
+                okm = res["pair_kf"][q].tolist() == exp_kf
+                cur = osub[q % ndist]
+                for slot, kf in enumerate(exp_kf):
+                    if kf < 0 or not okm:
+                        continue
+                    o_vec((kf % B) % ndist)
+                    obf = orc.match_bf(cur, osub[(kf % B) % ndist])
+                    okm = okm and np.array_equal(res["best"][q][slot][:len(cur)], (obf["distance"].astype(np.uint32) << 16) | obf["trainIdx"].astype(np.uint32))
+                check("%s frame %d association keys" % (tag, g), okm)
+        check_full_batch(kfdb.results(B), db1 - B, "full")
         # end to end: H2D + everything + D2H of the stereo results AND of the query hits / pair list / association keys, EVERY batch
         kfdb.reset()
         nf = len(fes)
@@ -447,6 +450,16 @@ def main():
         if dist is not None:
             kfdb.reset()
             nb_sh = min(nb_full, 16)
+            # every rank processes rank 0's frames here: a later shard then finds its best BoW hits among the OLDEST keyframes, which
+            # live on other ranks -- loop closures across the shard boundaries, the case the shared database exists for
+            fr_t = torch.from_numpy(np.ascontiguousarray(frames)).cuda(); dist.broadcast(fr_t, 0)
+            frames_sh = fr_t.cpu().numpy(); del fr_t
+            saved_cache = dict(oracle_cache)
+            if rank != 0:
+                oracle_cache.clear(); ovec.clear(); osub.clear()
+            frames_own = frames; frames = frames_sh                 # oracle_pair() reads `frames`
+            for f in rfe:
+                f.upload(frames_sh)
             starts = kfdb.connect(dist, [nb_sh * B] * world)
             barrier()
             t0 = time.perf_counter()
@@ -466,14 +479,20 @@ def main():
             ms_sh = allmax((t2 - t0) * 1e3)
             r_sh = kfdb.results(B)
             lo, hi = int(starts[rank]), int(starts[rank + 1])
+            check_full_batch(r_sh, hi - B, "sharded rank %d" % rank)
             kfs = r_sh["pair_kf"][r_sh["pair_kf"] >= 0]
             remote = float(((kfs < lo) | (kfs >= hi)).mean()) if len(kfs) else 0.0
             rem = allmax(remote)
+            frames = frames_own
+            if rank != 0:
+                oracle_cache.clear(); oracle_cache.update(saved_cache)
+            for f in rfe:
+                f.upload(frames)
             full["sharded"] = {"metric": "stereo frames/sec, full front-end, frames sharded over %d GPUs, ONE keyframe database (peer stores read in-kernel over NVLink)" % world,
                                "value": world * B * nb_sh / (ms_sh * 1e-3), "insert_pass_ms": allmax((t1 - t0) * 1e3), "query_pass_ms": allmax((t2 - t1) * 1e3),
                                "frames_total": world * B * nb_sh, "remote_fraction_of_associated_keyframes_last_batch_max_over_ranks": rem,
                                "note": "two passes (insert all, barrier, query all) so that frame g sees exactly the entries < g: results identical to one rank "
-                                       "(tests/test_gpu_full_frontend.py::test_one_logical_database_over_ranks_equals_single_rank)"}
+                                       "(tests/test_gpu_full_frontend.py::test_one_logical_database_over_ranks_equals_single_rank); checked here against the oracle on every rank"}
         kfdb.close(); bow.close()
     for f in extra:
         f.close()
