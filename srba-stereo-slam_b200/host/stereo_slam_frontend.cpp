@@ -1,6 +1,7 @@
 #include "stereo_slam_frontend.h"
 #include <algorithm>
 #include <deque>
+#include <chrono>
 #include <fstream>
 
 using mrpt::poses::CPose3D;
@@ -81,10 +82,10 @@ bool CSubmapGraphBackend::keyframe_global_pose(TKeyFrameID id, CPose3D& out) con
 // =====================================================================================================================
 CSRBAStereoSLAMEstimator::CSRBAStereoSLAMEstimator()
     : m_last_kf_ID(0), m_last_match_ID(0), m_last_num_tracked_feats((size_t)UNINITIALIZED_TRACKED_NUMBER), m_max_rotation(0), m_max_translation(0),
-      m_max_rotation_limit(0), m_max_translation_limit(0), m_source(nullptr), m_rba(&m_default_backend), m_count(0), m_end_app(false), m_f_da(nullptr)
+      m_max_rotation_limit(0), m_max_translation_limit(0), m_source(nullptr), m_rba(&m_default_backend), m_count(0), m_end_app(false), m_f_da(nullptr), m_f_ls(nullptr)
 {
 }
-CSRBAStereoSLAMEstimator::~CSRBAStereoSLAMEstimator() { if (m_f_da) fclose(m_f_da); }
+CSRBAStereoSLAMEstimator::~CSRBAStereoSLAMEstimator() { if (m_f_da) fclose(m_f_da); if (m_f_ls) fclose(m_f_ls); }
 
 void CSRBAStereoSLAMEstimator::initialize(const mrpt::utils::CConfigFile& config)
 {
@@ -126,7 +127,7 @@ void CSRBAStereoSLAMEstimator::initialize(const mrpt::utils::CConfigFile& config
 void CSRBAStereoSLAMEstimator::performStereoSLAM()
 {
     if (!m_source) throw std::logic_error("CSRBAStereoSLAMEstimator: no image source set");
-    if (general_options.debug && !m_f_da) { srba_prepare_out_dir(); m_f_da = fopen("da.txt", "wt"); }
+    if (general_options.debug && !m_f_da) { srba_prepare_out_dir(); m_f_da = fopen("da.txt", "wt"); m_f_ls = fopen("ls.txt", "wt"); }
     mrpt::obs::CObservationStereoImagesPtr stImgs;
     while ((stImgs = m_source->getNextFrame()).present() && !m_end_app) {
         VERBOSE_LEVEL(1) << std::endl << " >> Frame # " << m_count << std::endl;
@@ -137,6 +138,28 @@ void CSRBAStereoSLAMEstimator::performStereoSLAM()
         if ((general_options.max_num_kfs > 0 && m_keyframes.size() == (size_t)general_options.max_num_kfs) ||
             (general_options.to_step != 0 && m_count >= (size_t)general_options.to_step))
             m_end_app = true;
+    }
+    writeShutdownFiles();
+}
+
+// time_new_kf.txt: "<ms in define_new_keyframe> <observations>" per keyframe (EST.cpp:939-942); out_kf_poses.txt: "kf x y z yaw pitch roll",
+// %.3f (EST.cpp:977-986) -- the reference writes the poses of its final global pose-graph optimisation there, here they are the
+// backend's keyframe poses (no optimiser behind the stand-in backend: dead reckoning).
+void CSRBAStereoSLAMEstimator::writeShutdownFiles()
+{
+    if (!general_options.debug) return;
+    if (FILE* f = fopen("time_new_kf.txt", "wt")) {
+        for (const auto& st : m_stats) fprintf(f, "%.3f %d\n", 1000.0 * st.first, (int)st.second);
+        fclose(f);
+    }
+    if (FILE* f = fopen("out_kf_poses.txt", "wt")) {
+        for (size_t kf = 0; kf < m_keyframes.size(); ++kf) {
+            CPose3D p;
+            if (!m_rba->keyframe_global_pose(kf, p)) continue;
+            double yaw, pitch, roll; p.getYawPitchRoll(yaw, pitch, roll);
+            fprintf(f, "%d %.3f %.3f %.3f %.3f %.3f %.3f\n", (int)kf, p.x(), p.y(), p.z(), yaw, pitch, roll);
+        }
+        fclose(f);
     }
 }
 
@@ -160,7 +183,9 @@ void CSRBAStereoSLAMEstimator::processFirstFrame(const mrpt::obs::CObservationSt
     std::vector<TObservation> listObs;
     assembleObservations(new_kf, srba_options, listObs);
     std::vector<std::pair<TKeyFrameID, TKeyFrameID>> edges;
+    const auto t0 = std::chrono::steady_clock::now();
     m_rba->define_new_keyframe(listObs, false, CPose3D(), edges);          // not optimised the first time
+    m_stats.push_back(std::make_pair(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), listObs.size()));
     m_obs_log.push_back(listObs); m_kf_frame.push_back(m_count);
     m_last_kf_pose = new_kf.m_camera_pose;
 }
@@ -321,7 +346,10 @@ void CSRBAStereoSLAMEstimator::insertKeyframe(CStereoSLAMKF& new_kf, const TVect
     const CPose3D inputPose = srba_options.use_initial_pose ? CPose3D(m_incr_pose_from_last_kf) : CPose3D();
     std::vector<std::pair<TKeyFrameID, TKeyFrameID>> edges;
     VERBOSE_LEVEL(1) << "	Inserting " << listObs.size() << " observations in srba-slam engine" << std::endl;
-    m_rba->define_new_keyframe(listObs, true, inputPose, edges);                                        // EST.cpp:773-782
+    const auto t0 = std::chrono::steady_clock::now();
+    const TKeyFrameID new_id = m_rba->define_new_keyframe(listObs, true, inputPose, edges);             // EST.cpp:773-782
+    m_stats.push_back(std::make_pair(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), listObs.size()));
+    if (m_f_ls) fprintf(m_f_ls, "%d %.4f\n", (int)new_id, m_rba->last_obs_rmse());                      // ls.txt, EST.cpp:789-790
     m_obs_log.push_back(listObs); m_kf_frame.push_back(m_count);
 
     CPose3D kf_pose;                                                                                     // EST.cpp:881-916

@@ -37,6 +37,8 @@ public:
     virtual bool spanning_tree_pose(TKeyFrameID root, TKeyFrameID id, mrpt::poses::CPose3D& out) const = 0;
     // the new keyframe's pose as the GUI path reads it (build_opengl_representation, span_tree_max_depth = 1000; EST.cpp:881-895)
     virtual bool keyframe_global_pose(TKeyFrameID id, mrpt::poses::CPose3D& out) const = 0;
+    // newKFInfo.optimize_results_stg1.obs_rmse of the last define_new_keyframe (ls.txt, EST.cpp:790); 0 when there is no optimiser
+    virtual double last_obs_rmse() const { return 0.0; }
     virtual void loopClosureDetected(bool value = true) = 0;                                               // EST.cpp:501, 523, 545
     virtual void setLoopClosureOldID(TKeyFrameID id) = 0;                                                  // EST.cpp:502
 };
@@ -129,5 +131,7 @@ private:
     size_t m_count; bool m_end_app;
     std::vector<std::vector<TObservation>> m_obs_log; std::vector<size_t> m_kf_frame; std::vector<TKfCheckRecord> m_checks;
     std::vector<mrpt::poses::CPose3DRotVec> m_frame_pose;
-    FILE* m_f_da;                                                      // da.txt (EST.cpp:40, 649)
+    FILE* m_f_da; FILE* m_f_ls;                                        // da.txt, ls.txt (EST.cpp:40-41, 649, 790)
+    std::vector<std::pair<double, size_t>> m_stats;                    // (seconds in define_new_keyframe, observations): time_new_kf.txt (EST.cpp:170, 785, 939-942)
+    void writeShutdownFiles();                                         // time_new_kf.txt, out_kf_poses.txt (EST.cpp:939-942, 977-986)
 };

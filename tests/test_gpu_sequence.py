@@ -281,3 +281,52 @@ def test_reference_loop_runs_on_the_gpu_through_the_drop_in_headers(tmp_path, vo
     finally:
         L.ref_vo_close(h)
     assert repeats >= 1
+
+
+def test_debug_dump_formats(tmp_path, voc):
+    """[APP_OPTIONS] debug = true: the ten text artefacts of SURVEY.md Appendix C with the reference's formats -- info_kf / info_feats_kf
+    (CStereoSLAMKF.cpp:60-110), if_raw_match / if_match_after (EST.cpp:1455-1473, 1650-1689), da_dist (:602, :614), da_info (:749-764),
+    da.txt (:649), ls.txt (:790), time_new_kf.txt (:939-942), out_kf_poses.txt (:977-986) -- cross-checked against the binary dump of the same run."""
+    from srba_stereo_slam_b200 import synth
+    W, H, NF = 640, 192, 24
+    sc = synth.CorridorScene(seed=6, width=W, height=H, loop_radius=40.0)
+    frames = sc.sequence(NF)
+    fb = tmp_path / "frames.bin"; frames.tofile(fb)
+    vy = tmp_path / "voc.yml"; write_voc_yml(voc, vy)
+    out = tmp_path / "out"
+    ini = tmp_path / "k.ini"
+    ini.write_text(KITTI_INI.format(out_dir=str(out), debug="true", voc=str(vy), W=W, H=H, cx=float(sc.cx), cy=float(sc.cy), fx=float(sc.fx), fy=float(sc.fy), b=float(sc.b)))
+    ob = tmp_path / "seq.bin"
+    r = subprocess.run([os.path.join(HOST, "slam_sequence"), str(ini), str(fb), str(W), str(H), str(NF), str(ob)], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    lists, kf_frames, checks, poses = parse_sequence_dump(ob)
+    nkf = len(lists)
+    assert nkf >= 3
+    for k in range(nkf):
+        rows = [l.split() for l in open(out / ("info_kf%04d.txt" % k)).read().splitlines()]
+        assert rows[0][0] == "%" and len(rows) - 1 == len(lists[k])
+        for row, o in zip(rows[1:], lists[k]):
+            assert int(row[0]) == k and int(row[1]) == int(o["id"]) and [float(v) for v in row[2:6]] == [round(float(v), 2) for v in o["px"]]
+        feats = open(out / ("info_feats_kf%04d.txt" % k)).read().split()
+        nl, nr = int(feats[0]), int(feats[1]); assert len(feats) == 2 + 2 * (nl + nr)
+        if k > 0:
+            da = [l.split() for l in open(out / ("da_info_%04d.txt" % k)).read().splitlines()]
+            assert [int(r_[0]) for r_ in da] == [int(v) for v in lists[k]["id"]]
+            assert [[float(v) for v in r_[1:]] for r_ in da] == [[round(float(v), 2) for v in o["px"]] for o in lists[k]]
+            dd = open(out / ("da_dist_kf%04d.txt" % k)).read().splitlines()
+            assert len(dd) == len(lists[k])                      # one line per stereo match: the tracked distance, or 0.00 for a new landmark
+    ins = [c for c in checks if c["flags"] & 32]
+    for c in ins:                                                # one raw / filtered match file per associated keyframe
+        for kf, _ in c["tracked"]:
+            raw = open(out / ("if_raw_match_kf%04d_with_kf%04d.txt" % (c["cand"], kf))).read().splitlines()
+            assert raw[0].startswith("% OTHER_LX") and all(len(l.split()) == 5 for l in raw[1:])
+    after = [f for f in os.listdir(out) if f.startswith("if_match_after_")]
+    assert after and all(len(l.split()) == 6 for l in open(out / after[0]).read().splitlines()[1:])
+    da_txt = [l.split() for l in open(tmp_path / "da.txt").read().splitlines()]
+    assert sum(len(c["tracked"]) for c in ins) == len(da_txt) and all(len(r_) == 3 for r_ in da_txt)
+    ls = [l.split() for l in open(tmp_path / "ls.txt").read().splitlines()]
+    assert [int(r_[0]) for r_ in ls] == list(range(1, nkf))
+    tk = [l.split() for l in open(tmp_path / "time_new_kf.txt").read().splitlines()]
+    assert [int(r_[1]) for r_ in tk] == [len(l) for l in lists]
+    kp = [l.split() for l in open(tmp_path / "out_kf_poses.txt").read().splitlines()]
+    assert [int(r_[0]) for r_ in kp] == list(range(nkf)) and all(len(r_) == 7 for r_ in kp)
