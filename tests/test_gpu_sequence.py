@@ -14,7 +14,6 @@ import ctypes as C
 import os
 import struct
 import subprocess
-from concurrent.futures import ProcessPoolExecutor
 import numpy as np
 import pytest
 
@@ -106,24 +105,16 @@ LS = dict(initial_max_iters=30, max_iters=30, max_incr_cost=3, residual_threshol
           use_robust_kernel=True, kernel_param=2.0)
 
 
-def _render(args):
-    from srba_stereo_slam_b200 import synth
-    seed, W, H, radius, k = args
-    return synth.CorridorScene(seed=seed, width=W, height=H, loop_radius=radius).frame(k)
-
-
-def render_sequence(n, W, H, radius, seed):
-    jobs = [(seed, W, H, radius, k) for k in range(n)]
-    workers = max(1, min(len(os.sched_getaffinity(0)), 32))
-    if workers == 1 or n < 8:
-        fr = [_render(j) for j in jobs]
-    else:
-        with ProcessPoolExecutor(workers) as ex:
-            fr = list(ex.map(_render, jobs, chunksize=2))
-    out = np.zeros((n, 2, H, W), np.uint8)
-    for i, (l, r) in enumerate(fr):
-        out[i, 0], out[i, 1] = l, r
-    return out
+def render_sequence(n, W, H, radius, seed, tmp_path):
+    """Renders in a fresh child process (which forks its own worker pool): forking workers from the multi-threaded pytest process
+    itself risks a deadlock."""
+    import sys
+    out = tmp_path / "render.bin"
+    synth_py = os.path.join(ROOT, "srba-stereo-slam_b200", "synth.py")
+    subprocess.check_call([sys.executable, synth_py, str(n), str(W), str(H), repr(float(radius)), str(seed), str(out)], timeout=1500)
+    fr = np.fromfile(out, np.uint8).reshape(n, 2, H, W)
+    os.remove(out)
+    return fr
 
 
 def write_voc_yml(voc, path):
@@ -160,7 +151,7 @@ def run_sequence_case(tmp_path, voc, W, H, NF, radius, seed):
     from srba_stereo_slam_b200 import synth
     from oracle import slam_oracle as so
     sc = synth.CorridorScene(seed=seed, width=W, height=H, loop_radius=radius)
-    frames = render_sequence(NF, W, H, radius, seed)
+    frames = render_sequence(NF, W, H, radius, seed, tmp_path)
     fb = tmp_path / "frames.bin"; frames.tofile(fb)
     vy = tmp_path / "voc.yml"; write_voc_yml(voc, vy)
     ini = tmp_path / "kitti_synth.ini"
