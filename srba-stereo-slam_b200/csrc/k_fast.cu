@@ -12,7 +12,7 @@
 // blockIdx.y -> image.  A CTA (128x32 keypoint tile) stages its 142x40 pixel footprint with one 3-D TMA load, then:
 //   A.  SWAR quick reject, 4 pixels per thread-word (VABSDIFF4 + byte-parallel compares) on the opposite
 //       pairs (0,8) and (4,12); a thread owns one word column of 4 adjacent rows (10 loads feed 4 tests, no
-//       branches); survivors are compacted into a shared list (one atomic per thread + bit loop);
+//       branches); survivors are compacted into a shared list (one atomic per warp + straight-line predicated stores);
 //   B.  exact corner strength of the survivors, both polarities at once in packed s16x2 (one IMAD per ring
 //       pixel, VIMNMX3.S16x2 window min); corners get their score and go to a warp-private list (no atomics);
 //   C.  3x3 strict NMS evaluated only at the corners; survivors are appended to the per-(image,level)
@@ -44,7 +44,10 @@ __device__ __forceinline__ int lane0_atom_add_global(int* p, int v, int lane)
     return __shfl_sync(0xffffffffu, old, 0);
 }
 
-__global__ void __launch_bounds__(256, 6)
+#ifndef FAST_OCC
+#define FAST_OCC 7                       // 32 registers, 30.9 KB of shared memory: seven CTAs per SM (measured against 6: -0.8 %)
+#endif
+__global__ void __launch_bounds__(256, FAST_OCC)
 fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_tab, uint32_t* __restrict__ raw,
             int32_t* __restrict__ raw_count, const int th)
 {
@@ -121,24 +124,30 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
         }
         // halo words: NMS only reads the pixel column next to the tile (byte 3 of word 0, byte 0 of word 33)
         if (ok4) cm |= (quick(tw + (r4 + 3) * FAST_TP + j4) & (tid < 64 ? 0xfu : (j4 == 0 ? 0x8u : 0x1u))) << 16;
-        // compaction: one shared atomic per thread that has survivors (ptxas aggregates same-address atomics across the
-        // warp), then a short bit loop.  (A row-major warp-scan compaction was measured: fewer bank conflicts in phase B,
-        // 1.68 vs 1.78 wavefronts per ring load, but 46 more instructions per warp - no gain.)
-        // compaction: one shared atomic per thread that has survivors (ptxas aggregates same-address atomics across the warp), then
-        // the 20 flag bits are written by straight-line predicated stores -- a running offset instead of a data-dependent
-        // ffs/clear loop, whose trip count was the warp's worst lane (survivors cluster in textured regions: 123 -> ~85
-        // instructions per warp).  (A row-major warp-scan compaction was measured: fewer bank conflicts in phase B,
-        // 1.68 vs 1.78 wavefronts per ring load, but 46 more instructions per warp - no gain.)
+        // compaction: one shared atomic per thread that has survivors (ptxas aggregates same-address atomics across the warp: one
+        // scan + one ATOMS), then the 20 flag bits are written by straight-line predicated stores through a running shared
+        // ADDRESS: per bit one predicate, one value add, @p STS, @p address += 2 (inline PTX: the C++ form `list1[o++]`
+        // recomputed the list base on the uniform datapath for every bit, ~9 instructions per bit; 0.479 -> 0.461 ms).
+        // Measured dead ends: a data-dependent ffs/clear loop (trip count = the warp's worst lane, survivors cluster:
+        // 0.498 ms), a row-major warp-scan compaction (fewer bank conflicts in phase B, 46 more instructions per warp),
+        // skipping the quick test for warps whose rows lie below the ROI (0.479 -> 0.490 ms: the branch costs more than the
+        // 5 % of rows it saves).  Not built, by estimate only: one item per thread + a separate expansion pass (the
+        // expansion's trip count is again the warp's worst lane: ~66 M instead of ~72 M warp instructions, plus a barrier).
         if (cm) {
-            int o = atomicAdd(&n1, __popc(cm));
+            uint32_t a = smem_u32(list1) + 2u * (uint32_t)atomicAdd(&n1, __popc(cm));
 #pragma unroll
             for (int b = 0; b < 16; ++b) {
-                if (cm & (1u << b)) list1[o++] = (uint16_t)(pos0 + (b >> 2) * FAST_BOX_W + (b & 3));
+                const uint16_t v = (uint16_t)(pos0 + (b >> 2) * FAST_BOX_W + (b & 3));
+                asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u16 [%0], %1; @q add.u32 %0, %0, 2; }"
+                             : "+r"(a) : "h"(v), "r"(cm & (1u << b)) : "memory");
             }
             if (cm >> 16) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (cm & (0x10000u << b)) list1[o++] = (uint16_t)(pos4 + b);
+                for (int b = 0; b < 4; ++b) {
+                    const uint16_t v = (uint16_t)(pos4 + b);
+                    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u16 [%0], %1; @q add.u32 %0, %0, 2; }"
+                                 : "+r"(a) : "h"(v), "r"(cm & (0x10000u << b)) : "memory");
+                }
             }
         }
     }
