@@ -226,7 +226,9 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
 #define FZ_ROWS 44                       // 43 rows + one spare (the last row pair is (42, 43))
 #define FZ_PITCH 88                      // bytes: 8 pad | 56 data | 24 pad; 22 words: consecutive row PAIRS land 12 banks apart (row pass: lanes span 4 pairs x 10 groups)
 #define FZ_PAIRS 22
-#define FZ_KPW 4                         // keypoint slots a warp describes in turn
+#ifndef FZ_KPW
+#define FZ_KPW 8                         // keypoint slots a warp describes in turn (2: 0.424, 4: 0.404, 8: 0.400, 16: 0.412 ms)
+#endif
 #define FZ_WARPS 6                       // 6 x 7.2 KB of patch buffers per CTA: five CTAs (30 warps) per SM
 #define FZ_GROUPS 10                     // 4-column output groups covering x-18 .. x+18 for every alignment
 #define FZ_RB_PITCH (FZ_GROUPS * 4)      // row-sum words per row pair

@@ -228,6 +228,7 @@ static int create_impl(sfe_context* c)
             build_resize_table(P.g[l - 1].w, P.g[l].w, true, c->xtab[l]);
             build_resize_table(P.g[l - 1].h, P.g[l].h, false, c->ytab[l]);
         }
+        if ((P.g[l].w + PYR_TW - 1) / PYR_TW > PYR_MAX_TILES || (P.g[l].h + PYR_TH - 1) / PYR_TH > PYR_MAX_TILES) { c->err = "image too large for the pyramid kernel's tile tables"; return SFE_ERR_INVALID; }
         // footprint check against the fixed TMA box
         for (int x0 = 0; x0 < P.g[l].w; x0 += PYR_TW) {
             const int x1 = std::min(x0 + PYR_TW, P.g[l].w) - 1;
@@ -258,8 +259,17 @@ static int create_impl(sfe_context* c)
             SFE_CUDA(c, dalloc(&c->d_gtab[l], gt.size()));
             SFE_CUDA(c, cudaMemcpy(c->d_gtab[l], gt.data(), gt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
-        SFE_CUDA(c, dalloc(&c->d_ytab[l], c->ytab[l].size()));
-        SFE_CUDA(c, cudaMemcpy(c->d_ytab[l], c->ytab[l].data(), c->ytab[l].size() * sizeof(int2), cudaMemcpyHostToDevice));
+        {   // vertical table as the kernel consumes it: both source rows clamped to the image, coefficients pre-shifted
+            const int sh = P.g[l - 1].h;
+            std::vector<int4> yt(c->ytab[l].size());
+            for (size_t y = 0; y < yt.size(); ++y) {
+                const int s = c->ytab[l][y].x, cf = c->ytab[l][y].y;
+                yt[y].x = std::min(std::max(s, 0), sh - 1) * (PYR_TW / 2) * 4; yt[y].y = std::min(std::max(s + 1, 0), sh - 1) * (PYR_TW / 2) * 4;
+                yt[y].z = (int)((uint32_t)(cf & 0xffff) << 16); yt[y].w = (int)((uint32_t)cf >> 16 << 16);
+            }
+            SFE_CUDA(c, dalloc(&c->d_ytab[l], yt.size()));
+            SFE_CUDA(c, cudaMemcpy(c->d_ytab[l], yt.data(), yt.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        }
     }
 
     // ---- TMA descriptors: one 3-D (x, y, image) map per level; the box is the largest any kernel
