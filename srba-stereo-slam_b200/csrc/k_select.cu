@@ -10,8 +10,12 @@
 // is an std::nth_element artefact, so parity is defined on this order.
 //
 // One CTA per (image, level).  Harris: one thread per candidate, 9x9 window via aligned word loads and a
-// 3-row sliding register window (integer sums, exact); survivors bitonic-sorted in shared memory;
-// the float expression is evaluated unfused (__fmul_rn/__fsub_rn) to match the CPU bit for bit.
+// 3-row sliding register window (integer sums, exact); the float expression is evaluated unfused
+// (__fmul_rn/__fsub_rn) to match the CPU bit for bit.  The kernel is latency-bound (a chain of short phases), so the
+// phases are arranged for few barriers (9 on the common path, was 55): every histogram is zeroed once at the start,
+// every warp evaluates the k-th-from-top scan itself (no broadcast through shared memory, no barrier after it), and
+// the canonical order comes from rank counting over the kept points (unique keys: rank = #smaller, broadcast
+// 128-bit shared loads, no barriers) instead of a 36-stage bitonic sort.
 #include "sfe_internal.cuh"
 
 #define SEL_SORT_CAP 1024
@@ -52,7 +56,10 @@ __device__ __forceinline__ void kth_from_top(const int* hist, int k, int lane, i
     above = __shfl_sync(0xffffffffu, ab, src);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
+#ifndef SEL_OCC
+#define SEL_OCC 4                        // 64 registers: four 256-thread CTAs per SM
+#endif
+__global__ void __launch_bounds__(SEL_THREADS, SEL_OCC)
 select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr,
               const uint32_t* __restrict__ raw, const int32_t* __restrict__ raw_count,
               uint32_t* __restrict__ sel_xy, float* __restrict__ sel_resp, int32_t* __restrict__ sel_count,
@@ -62,8 +69,11 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     uint32_t* cand_xy = dyn;                                    // [cand_cap]  (y<<16 | x)
     float* cand_resp = reinterpret_cast<float*>(dyn + cand_cap);// [cand_cap]
     __shared__ int hist[256];
-    __shared__ int s_n, s_thr, s_k;
+    __shared__ int histp[4][256];                               // radix-select passes of the Harris cut
+    __shared__ int s_n, s_n2, s_k;
     __shared__ uint32_t s_prefix;
+    __shared__ alignas(16) uint32_t skey[SEL_SORT_CAP];
+    __shared__ float sval[SEL_SORT_CAP];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int level = blockIdx.x, img = blockIdx.y;
@@ -74,28 +84,27 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     if (n > g.raw_cap) { n = g.raw_cap; if (tid == 0) atomicOr(&status[img], SFE_ERR_CAPACITY); }
 
     // ---- retainBest(2q) on the integer FAST score: histogram cut ---------------------------
-    for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-    if (tid == 0) s_n = 0;
+    for (int i = tid; i < 256; i += SEL_THREADS) { hist[i] = 0; histp[0][i] = 0; histp[1][i] = 0; histp[2][i] = 0; histp[3][i] = 0; }
+    for (int i = tid; i < SEL_SORT_CAP; i += SEL_THREADS) skey[i] = 0xffffffffu;     // padding of the rank-counting loop
+    if (tid == 0) { s_n = 0; s_n2 = 0; }
     __syncthreads();
     for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&hist[rl[i] >> 24], 1);
     __syncthreads();
-    if (warp == 0) {
-        int thr = 0, above = 0;
-        if (n > 2 * q) {
-            kth_from_top(hist, 2 * q, lane, thr, above);
-            if (q == 0) thr = 256;
-        }
-        if (lane == 0) { s_thr = thr; s_k = (n > 2 * q && thr < 256 && above + hist[thr] > cand_cap) ? cand_cap - above : -1; }
+    int thr = 0, kcut = -1;                                       // every warp evaluates the cut itself: identical values, no broadcast
+    if (n > 2 * q) {
+        int above = 0;
+        kth_from_top(hist, 2 * q, lane, thr, above);
+        if (q == 0) thr = 256;
+        if (thr < 256 && above + hist[thr] > cand_cap) kcut = cand_cap - above;
     }
-    __syncthreads();
-    const int thr = s_thr;
     // Ties at the cut that do not fit the shared candidate list (binary / saturated images: most corners score the
     // same): OpenCV would carry every tie into the Harris stage; here the ties are cut DETERMINISTICALLY to the ones
     // with the smallest (y, x) -- a 3-pass radix select on the inverted 24-bit position key -- instead of failing the
     // frame with an order-dependent truncation.
     uint32_t tie_max = 0x00ffffffu;
-    if (s_k >= 0) {
-        if (tid == 0) s_prefix = 0u;
+    if (kcut >= 0) {                                              // uniform, rare
+        __syncthreads();                                          // every warp has read hist[]
+        if (tid == 0) { s_prefix = 0u; s_k = kcut; }
         uint32_t mask = 0u;
         for (int shift = 16; shift >= 0; shift -= 8) {
             __syncthreads();
@@ -180,58 +189,50 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     // ---- retainBest(q) on the float response: radix select of the q-th largest ------------
     float boundary = -__int_as_float(0x7f800000);   // -inf: keep everything
     if (nc > q && q > 0) {
-        if (tid == 0) { s_prefix = 0u; s_k = q; }
-        uint32_t mask = 0u;
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
-            __syncthreads();
-            const uint32_t prefix = s_prefix;
+        uint32_t prefix = 0u, mask = 0u;
+        int kk = q;
+#pragma unroll 1
+        for (int p = 0; p < 4; ++p) {                             // one barrier per pass: histp[p] was zeroed at the start
+            const int shift = 24 - 8 * p;
             for (int i = tid; i < nc; i += SEL_THREADS) {
                 const uint32_t k = float_order_key(cand_resp[i]);
-                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+                if ((k & mask) == prefix) atomicAdd(&histp[p][(k >> shift) & 255u], 1);
             }
             __syncthreads();
-            if (warp == 0) {
-                int b, above;
-                kth_from_top(hist, s_k, lane, b, above);
-                __syncwarp();
-                if (lane == 0) { s_k = s_k - above; s_prefix = prefix | ((uint32_t)b << shift); }
-            }
-            mask |= 255u << shift;
-            __syncthreads();
+            int b, above;
+            kth_from_top(histp[p], kk, lane, b, above);           // every warp: same result
+            kk -= above; prefix |= (uint32_t)b << shift; mask |= 255u << shift;
         }
-        boundary = float_from_key(s_prefix);
+        boundary = float_from_key(prefix);
     } else if (q == 0) {
         nc = 0;
     }
 
-    // ---- canonical order (y, then x): compact the kept points, bitonic sort on the packed key -----------
+    // ---- canonical order (y, then x): compact the kept points, then rank counting on the packed key ----------
     uint32_t* out_xy = sel_xy + (size_t)img * P.sel_img_stride + g.sel_ofs;
     float* out_r = sel_resp + (size_t)img * P.sel_img_stride + g.sel_ofs;
-    __shared__ uint32_t skey[SEL_SORT_CAP];
-    __shared__ float sval[SEL_SORT_CAP];
     // Ties at the Harris cut that do not fit the selection list (identical structures repeated over the image: every response equal):
     // as at the FAST-score cut above, the ties with the smallest (y, x) are kept -- deterministic, and the frame succeeds.
     uint32_t harris_tie_max = 0xffffffffu;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (tid == 0) s_n = 0;
-        __syncthreads();
         for (int base = 0; base < nc; base += SEL_THREADS) {      // warp-aggregated compaction of the kept points
             const int i = base + tid;
             const bool kp = i < nc && (cand_resp[i] > boundary || (cand_resp[i] == boundary && cand_xy[i] <= harris_tie_max));
             const uint32_t bal = __ballot_sync(0xffffffffu, kp);
             if (bal) {
                 int wb = 0;
-                if (lane == 0) wb = atomicAdd(&s_n, __popc(bal));
+                if (lane == 0) wb = atomicAdd(&s_n2, __popc(bal));
                 wb = __shfl_sync(0xffffffffu, wb, 0);
                 const int slot = wb + __popc(bal & ((1u << lane) - 1u));
                 if (kp && slot < SEL_SORT_CAP) { skey[slot] = cand_xy[i]; sval[slot] = cand_resp[i]; }
             }
         }
         __syncthreads();
-        if (s_n <= g.sel_cap || attempt == 1) break;               // uniform
-        // overflow: need = sel_cap - #(response > boundary) ties; 4-pass radix select of the need-th smallest (y<<16|x) among the ties
-        if (tid == 0) { s_k = 0; s_prefix = 0u; }
+        if (s_n2 <= g.sel_cap || attempt == 1) break;              // uniform
+        // overflow (rare): need = sel_cap - #(response > boundary) ties; 4-pass radix select of the need-th smallest (y<<16|x) among the ties
+        __syncthreads();
+        if (tid == 0) { s_k = 0; s_prefix = 0u; s_n2 = 0; }
+        for (int i = tid; i < SEL_SORT_CAP; i += SEL_THREADS) skey[i] = 0xffffffffu;
         __syncthreads();
         int above = 0;
         for (int i = tid; i < nc; i += SEL_THREADS) above += cand_resp[i] > boundary;
@@ -261,26 +262,20 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
         }
         harris_tie_max = ~s_prefix;
     }
-    const int nk_all = s_n;
+    const int nk_all = s_n2;
     if (nk_all <= SEL_SORT_CAP) {
-        int np2 = 1; while (np2 < nk_all) np2 <<= 1;
-        for (int i = nk_all + tid; i < np2; i += SEL_THREADS) { skey[i] = 0xffffffffu; sval[i] = 0.f; }
-        __syncthreads();
-        for (int k = 2; k <= np2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < np2; i += SEL_THREADS) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const uint32_t ka = skey[i], kb = skey[ixj];
-                        const bool up = (i & k) == 0;
-                        if ((ka > kb) == up) { skey[i] = kb; skey[ixj] = ka; const float t = sval[i]; sval[i] = sval[ixj]; sval[ixj] = t; }
-                    }
-                }
-                __syncthreads();
+        // keys are unique (one per pixel): rank = number of smaller keys; entries past nk_all hold 0xffffffff and never count
+        for (int i = tid; i < nk_all; i += SEL_THREADS) {
+            const uint32_t key = skey[i];
+            int rank = 0;
+            for (int j = 0; j < nk_all; j += 4) {
+                const uint4 k4 = *reinterpret_cast<const uint4*>(skey + j);
+                rank += (int)(k4.x < key) + (int)(k4.y < key) + (int)(k4.z < key) + (int)(k4.w < key);
             }
-        for (int i = tid; i < min(nk_all, g.sel_cap); i += SEL_THREADS) { out_xy[i] = skey[i]; out_r[i] = sval[i]; }
+            if (rank < g.sel_cap) { out_xy[rank] = key; out_r[rank] = sval[i]; }
+        }
     } else {
-        // very large quotas: rank by counting (O(n^2), exact)
+        // very large quotas: rank by counting over the candidate list (O(n^2), exact)
         for (int i = tid; i < nc; i += SEL_THREADS) {
             const uint32_t key = cand_xy[i];
             if (!(cand_resp[i] > boundary || (cand_resp[i] == boundary && key <= harris_tie_max))) continue;
