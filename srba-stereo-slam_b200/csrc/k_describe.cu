@@ -229,12 +229,17 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
 #ifndef FZ_KPW
 #define FZ_KPW 8                         // keypoint slots a warp describes in turn (2: 0.424, 4: 0.404, 8: 0.400, 16: 0.412 ms)
 #endif
-#define FZ_WARPS 6                       // 6 x 7.2 KB of patch buffers per CTA: five CTAs (30 warps) per SM
+#ifndef FZ_WARPS
+#define FZ_WARPS 5                       // 5 x 7.2 KB of patch buffers per CTA: six CTAs (30 warps) per SM (measured: 2 warps 0.411, 3: 0.408, 4: 0.400, 5: 0.392, 6: 0.400, 10: 0.417, 15: 0.424 ms)
+#endif
+#ifndef FZ_CTAS
+#define FZ_CTAS 6
+#endif
 #define FZ_GROUPS 10                     // 4-column output groups covering x-18 .. x+18 for every alignment
 #define FZ_RB_PITCH (FZ_GROUPS * 4)      // row-sum words per row pair
 #define FZ_WARP_BYTES (FZ_ROWS * FZ_PITCH + FZ_PAIRS * FZ_RB_PITCH * 4)
 
-__global__ void __launch_bounds__(FZ_WARPS * 32, 5)
+__global__ void __launch_bounds__(FZ_WARPS * 32, FZ_CTAS)
 describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr,
                       const uint32_t* __restrict__ sel_xy, const float* __restrict__ sel_resp,
                       const int32_t* __restrict__ sel_count,
@@ -246,8 +251,8 @@ describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __rest
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.y;
     for (int t = tid; t < 256; t += FZ_WARPS * 32) pat_s[t] = reinterpret_cast<const uint32_t*>(d_brief_pattern)[8 * (t & 31) + (t >> 5)];
-    if (tid < 128) {
-        const int av = tid >> 3, k = tid & 7, m = c_umax[av];
+    for (int t = tid; t < 128; t += FZ_WARPS * 32) {
+        const int av = t >> 3, k = t & 7, m = c_umax[av];
         uint32_t mk = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) if (abs(4 * k + b - 15) <= m) mk |= 0xffu << (8 * b);

@@ -272,8 +272,7 @@ static int create_impl(sfe_context* c)
         }
     }
 
-    // ---- TMA descriptors: one 3-D (x, y, image) map per level; the box is the largest any kernel
-    //      asks for (FAST/blur 144x24, pyramid 160x24), every kernel loads the full box ---------------
+    // ---- TMA descriptors: 3-D (x, y, image) maps per level, one per box shape; every kernel loads its full box ----
     PFN_encodeTiled enc = nullptr;
     {
         void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
@@ -281,7 +280,7 @@ static int create_impl(sfe_context* c)
         if (!fn || qres != cudaDriverEntryPointSuccess) { c->err = "cuTensorMapEncodeTiled not available"; return SFE_ERR_CUDA; }
         enc = (PFN_encodeTiled)fn;
     }
-    // The box shape is baked into a map: pyr_map[] (160x24) serves FAST and blur, pyrsrc_map[] (176x24)
+    // The box shape is baked into a map: pyr_map[] (160x40) serves FAST and blur, pyrsrc_map[] (176x88)
     // the source side of the pyramid kernel.
     for (int l = 0; l < L; ++l) {
         const LevelGeom& g = P.g[l];

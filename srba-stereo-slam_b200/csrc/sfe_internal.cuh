@@ -36,7 +36,9 @@
 #define BLUR_BOX_H 40       // shares the 160x40 maps with FAST (rows 38,39 unused)
 #define BLUR_ROWS (BLUR_TH + 6)
 
+#ifndef SEL_THREADS
 #define SEL_THREADS 256
+#endif
 #define SEL_TIE_SLACK 64   // extra slots per level for Harris-response ties
 
 struct LevelGeom {
