@@ -258,6 +258,7 @@ describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __rest
         for (int b = 0; b < 4; ++b) if (abs(4 * k + b - 15) <= m) mk |= 0xffu << (8 * b);
         disc_mask[av * 9 + k] = mk;
     }
+    pdl_wait();                                                                  // the selection lists are the previous kernel's output
     __syncthreads();
 
     // slot -> (level, index): lanes 0..7 hold the per-level counts, an 8-lane scan gives the level boundaries (once per warp)
@@ -440,9 +441,8 @@ void launch_describe(sfe_context* c, int nimg)
 {
     if (describe_is_fused(c)) {
         dim3 grid((c->pack.kp_cap + FZ_WARPS * FZ_KPW - 1) / (FZ_WARPS * FZ_KPW), nimg);
-        describe_fused_kernel<<<grid, FZ_WARPS * 32, FZ_WARPS * FZ_WARP_BYTES, c->stream>>>(c->pack, c->d_pyr, c->d_sel_xy, c->d_sel_resp,
-                                                                                              c->d_sel_count, c->d_kp, c->d_desc, c->d_kp_count);
-        c->launches++;
+        sfe_launch(c, (c->pdl_mask & 8) != 0, describe_fused_kernel, grid, dim3(FZ_WARPS * 32), FZ_WARPS * FZ_WARP_BYTES, c->pack, (const uint8_t*)c->d_pyr, (const uint32_t*)c->d_sel_xy,
+                   (const float*)c->d_sel_resp, (const int32_t*)c->d_sel_count, c->d_kp, c->d_desc, c->d_kp_count);
         return;
     }
     dim3 grid((c->pack.kp_cap + DESC_WARPS - 1) / DESC_WARPS, nimg);

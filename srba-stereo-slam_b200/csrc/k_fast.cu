@@ -72,6 +72,7 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     // BEFORE the issue: 5 % of the warp samples waited there)
     if (tid == 0) {
         mbar_init(&bar, 1); fence_mbar_init(); n1 = 0;
+        pdl_wait();                                               // the pyramid is the previous kernels' output
         mbar_arrive_expect_tx(&bar, FAST_BOX_H * FAST_BOX_W);
         tma_load_3d(tile, &P.pyr_map[level], bx0, ty0 - 4, img, &bar);
     }
@@ -96,6 +97,7 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
 #pragma unroll
     for (int k = 0; k < 4; ++k) sw[(pos0 >> 2) + k * FAST_TP] = 0u;
     if (in4) sw[pos4 >> 2] = 0u;
+    pdl_wait();                                                   // every thread, before the tile and the raw lists
     __syncthreads();                                              // mbarrier initialised, n1 = 0
     mbar_wait(&bar, 0);
 
@@ -246,6 +248,5 @@ void launch_fast(sfe_context* c, int nimg)
     const int ntiles = c->pack.ftile_prefix[c->pack.nlevels];
     if (ntiles == 0) return;
     dim3 grid(ntiles, nimg);
-    fast_kernel<<<grid, 256, 0, c->stream>>>(c->pack, c->d_ftile_tab, c->d_raw, c->d_raw_count, c->fast_th);
-    c->launches++;
+    sfe_launch(c, c->pack.nlevels > 1 && (c->pdl_mask & 2), fast_kernel, grid, dim3(256), 0, c->pack, (const int4*)c->d_ftile_tab, c->d_raw, c->d_raw_count, c->fast_th);
 }

@@ -51,6 +51,7 @@ rowband_match_kernel(const RowBandArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.y;
     const int il = 2 * pair, ir = 2 * pair + 1;
+    pdl_wait();                                                   // keypoints and descriptors are the previous kernel's output
     const int nl = min(a.kp_count[il], a.kp_cap), nr = min(a.kp_count[ir], a.kp_cap);
     const sfe_keypoint* kl = a.kps + (size_t)il * a.kp_cap;
     const sfe_keypoint* kr = a.kps + (size_t)ir * a.kp_cap;
@@ -129,6 +130,7 @@ rowband_compact_kernel(const RowBandArgs a)
     __shared__ int s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.x;
+    pdl_wait();
     const int nl = min(a.kp_count[2 * pair], a.kp_cap);
     const uint32_t* best = a.best + (size_t)pair * a.kp_cap;
     const uint32_t* owner = a.owner + (size_t)pair * a.kp_cap;
@@ -184,9 +186,8 @@ void launch_match_rowband(sfe_context* c, int npairs)
     // enough CTAs to fill the GPU (2 waves of 148 SMs) however small the batch, at least 64 left keypoints per slice
     a.slices = std::max(1, std::min({ (888 + npairs - 1) / npairs, (c->cfg.nfeatures + 63) / 64, 32 }));
     if (a.robust) cudaMemsetAsync(c->d_rb_owner, 0xff, sizeof(uint32_t) * (size_t)npairs * a.kp_cap, c->stream);
-    rowband_match_kernel<<<dim3(a.slices, npairs), RB_THREADS, rowband_smem(c), c->stream>>>(a);
-    rowband_compact_kernel<<<npairs, RB_THREADS, 0, c->stream>>>(a);
-    c->launches += 2;
+    sfe_launch(c, !a.robust && (c->pdl_mask & 16), rowband_match_kernel, dim3(a.slices, npairs), dim3(RB_THREADS), rowband_smem(c), a);     // robust: a memset precedes it
+    sfe_launch(c, (c->pdl_mask & 32) != 0, rowband_compact_kernel, dim3(npairs), dim3(RB_THREADS), 0, a);
 }
 
 // ------------------------------------------------------------------------------------------------

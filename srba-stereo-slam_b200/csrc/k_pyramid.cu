@@ -50,6 +50,7 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     const int sy0 = a.tile_sy[blockIdx.y];        // first source row of the tile
     if (tid == 0) {
         mbar_init(&bar, 1); fence_mbar_init();
+        pdl_wait();                                   // the source level is the previous kernel's output
         mbar_arrive_expect_tx(&bar, PYR_BOX_H * PYR_BOX_W);
         tma_load_3d(tile, &src_map, bx0, sy0, img, &bar);
     }
@@ -65,6 +66,7 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     const int nrows = a.tile_nr[blockIdx.y];      // source rows this tile really needs: [sy0, second source row of the last destination row]
     const uint32_t* row = tile + rr * PYR_TPW + (off >> 2);
     uint32_t* hrow = hbuf + rr * PYR_HPW + 2 * gq;
+    pdl_wait();                                                         // every thread, before it touches the tile or stores
     __syncthreads();                                                    // mbarrier initialised (thread 0), yts visible
     mbar_wait(&bar, 0);
 
@@ -129,9 +131,9 @@ void launch_pyramid_level(sfe_context* c, int level, int nimg)
         a.tile_sy[t] = (short)s0; a.tile_nr[t] = (short)(s1 - s0 + 1);
     }
     dim3 grid((g.w + PYR_TW - 1) / PYR_TW, (g.h + PYR_TH - 1) / PYR_TH, nimg);
-    if (c->cfg.pyramid_mode == SFE_PYRAMID_CV4_EXACT) pyramid_kernel<SFE_PYRAMID_CV4_EXACT><<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
-    else pyramid_kernel<SFE_PYRAMID_CV24_LINEAR><<<grid, 256, 0, c->stream>>>(c->pyrsrc_map[level - 1], a);
-    c->launches++;
+    const bool dep = level > 1 && (c->pdl_mask & 1);                       // level 1 follows the counter memset (not a kernel) or the upload
+    if (c->cfg.pyramid_mode == SFE_PYRAMID_CV4_EXACT) sfe_launch(c, dep, pyramid_kernel<SFE_PYRAMID_CV4_EXACT>, grid, dim3(256), 0, c->pyrsrc_map[level - 1], a);
+    else sfe_launch(c, dep, pyramid_kernel<SFE_PYRAMID_CV24_LINEAR>, grid, dim3(256), 0, c->pyrsrc_map[level - 1], a);
 }
 
 // ---- level 0 ingest: tightly packed host layout [img][H][W] -> pitched level-0 arena -----------------------

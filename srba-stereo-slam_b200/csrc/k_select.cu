@@ -80,13 +80,15 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     const LevelGeom& g = P.g[level];
     const int q = g.quota;
     const uint32_t* rl = raw + (size_t)img * P.raw_img_stride + g.raw_ofs;
+    // shared-memory set-up first: it does not depend on the FAST kernel, whose tail this CTA may be running under
+    for (int i = tid; i < 256; i += SEL_THREADS) { hist[i] = 0; histp[0][i] = 0; histp[1][i] = 0; histp[2][i] = 0; histp[3][i] = 0; }
+    for (int i = tid; i < SEL_SORT_CAP; i += SEL_THREADS) skey[i] = 0xffffffffu;     // padding of the rank-counting loop
+    if (tid == 0) { s_n = 0; s_n2 = 0; }
+    pdl_wait();
     int n = raw_count[(size_t)img * P.nlevels + level];
     if (n > g.raw_cap) { n = g.raw_cap; if (tid == 0) atomicOr(&status[img], SFE_ERR_CAPACITY); }
 
     // ---- retainBest(2q) on the integer FAST score: histogram cut ---------------------------
-    for (int i = tid; i < 256; i += SEL_THREADS) { hist[i] = 0; histp[0][i] = 0; histp[1][i] = 0; histp[2][i] = 0; histp[3][i] = 0; }
-    for (int i = tid; i < SEL_SORT_CAP; i += SEL_THREADS) skey[i] = 0xffffffffu;     // padding of the rank-counting loop
-    if (tid == 0) { s_n = 0; s_n2 = 0; }
     __syncthreads();
     for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&hist[rl[i] >> 24], 1);
     __syncthreads();
@@ -301,8 +303,6 @@ void launch_select(sfe_context* c, int nimg)
     const int cap = c->sel_cand_cap;
     const size_t smem = (size_t)cap * 8;
     dim3 grid(c->pack.nlevels, nimg);
-    select_kernel<<<grid, SEL_THREADS, smem, c->stream>>>(c->pack, c->d_pyr, c->d_raw, c->d_raw_count,
-                                                           c->d_sel_xy, c->d_sel_resp, c->d_sel_count,
-                                                           c->d_status, cap);
-    c->launches++;
+    sfe_launch(c, (c->pdl_mask & 4) != 0, select_kernel, grid, dim3(SEL_THREADS), smem, c->pack, (const uint8_t*)c->d_pyr, (const uint32_t*)c->d_raw, (const int32_t*)c->d_raw_count,
+               c->d_sel_xy, c->d_sel_resp, c->d_sel_count, c->d_status, cap);
 }

@@ -187,6 +187,8 @@ static int create_impl(sfe_context* c)
     SFE_CUDA(c, dalloc(&c->d_pyr, arena));
     SFE_CUDA(c, cudaMemset(c->d_pyr, 0, arena));
     c->force_unfused = getenv("SFE_FORCE_UNFUSED_BLUR") != nullptr;
+    c->pdl = getenv("SFE_NO_PDL") == nullptr;
+    if (getenv("SFE_PDL_MASK")) c->pdl_mask = atoi(getenv("SFE_PDL_MASK"));
     if (!describe_is_fused(c)) {           // the blurred arena only exists where a separate blur kernel runs (float mode, edge_threshold < 22)
         SFE_CUDA(c, dalloc(&c->d_blur, arena));
         SFE_CUDA(c, cudaMemset(c->d_blur, 0, arena));

@@ -15,7 +15,11 @@ import sys
 ROOT = os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def child(lib):
+def child(spec):
+    # "path/lib.so@VAR=VALUE" sets an environment knob of the library (e.g. SFE_NO_PDL=1) for this child only
+    lib, _, knob = spec.partition("@")
+    if knob:
+        k, _, v = knob.partition("="); os.environ[k] = v
     sys.path.insert(0, ROOT)
     import numpy as np
     from srba_stereo_slam_b200 import frontend, synth
@@ -53,7 +57,7 @@ def child(lib):
         for a in fe.get_values(p):
             h.update(np.ascontiguousarray(a).tobytes())
     fe.close(); fe2.close()
-    print("VB_RESULT " + json.dumps({"lib": lib, "stages_ms": med, "step_ms": step_ms, "digest": h.hexdigest()[:16]}))
+    print("VB_RESULT " + json.dumps({"lib": spec, "stages_ms": med, "step_ms": step_ms, "digest": h.hexdigest()[:16]}))
 
 
 def main():
