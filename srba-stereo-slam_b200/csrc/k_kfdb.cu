@@ -205,8 +205,8 @@ __global__ void kf_query_prep_kernel(const int32_t* __restrict__ dbw, const doub
 // ---- 5. exact L1 scores: lane = query (32 per CTA), warp = database entry ------------------------------------------
 // Word-major hit masks per tile: ONE lookup T[w] tells which of the 32 queries contain word w.  A warp reads 32
 // consecutive words of the entry (coalesced), looks their masks up, transposes the 32x32 bit matrix across the lanes
-// (5 shuffle stages) so that lane q holds query q's hits, then walks the chunk's words in ascending order, four at a
-// time: word id and entry value by shuffle, the query value by one predicated gather, FP64 accumulation in ascending
+// (5 shuffle stages) so that lane q holds query q's hits, and every lane replays its own hits in ascending word order:
+// word id and entry value by shuffle, the query value by one predicated gather, FP64 accumulation in ascending
 // word order = DBoW2's order (bit-identical scores).  No shared memory, no queues.
 #define KS_WARPS 8
 
@@ -253,27 +253,24 @@ kf_score_kernel(const __grid_constant__ KfPeers P, int cap,
             const int i = c0 + lane;
             int w = 0; double dv = 0.0; uint32_t m = 0u;
             if (i < n) { w = __ldg(ew + i); dv = __ldg(ev + i); m = __ldg(T + w); }      // m: which queries contain word w
-            const uint32_t tm = transpose32(m, lane);                 // lane q: which of the chunk's 32 words hit query q
-            const uint32_t anyhit = __reduce_or_sync(0xffffffffu, tm);
+            uint32_t tm = transpose32(m, lane);                       // lane q: which of the chunk's 32 words hit query q
             any |= tm != 0u;
-            // words in ascending order (= DBoW2's accumulation order), four at a time: the entry's word id and value come
-            // by shuffle from the lane that loaded them, the query's value is one predicated gather; groups without any
-            // hit in the whole tile are skipped warp-uniformly.  (Prefetching the next chunks' words/masks was measured:
-            // no gain - the exposed latency is in the gathers.)
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                if (((anyhit >> (4 * g)) & 0xfu) == 0u) continue;
-                double qv[4], dj[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int j = 4 * g + k;
-                    const int wj = __shfl_sync(0xffffffffu, w, j);
-                    dj[k] = __shfl_sync(0xffffffffu, dv, j);
-                    qv[k] = ((tm >> j) & 1u) ? __ldg(myq + wj) : 0.0;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((tm >> (4 * g + k)) & 1u) s += fabs(qv[k] - dj[k]) - fabs(qv[k]) - fabs(dj[k]);
+            // Every lane replays ITS OWN hits, lowest bit first = ascending word order (DBoW2's accumulation order): the entry's
+            // word id and value come by shuffle from the lane that loaded them (a different source lane per lane), the query's
+            // value is one predicated gather.  A lane has ~0.6 hits per 32-word chunk, the warp's worst lane ~3: the trip count
+            // is that maximum, two hits per trip so that both gathers are in flight together.  (Round 1 walked all 32 words four
+            // at a time for every lane - 2 % of those lane-slots held a hit: ~250 instead of ~35 instructions per chunk.  The
+            // kernel stays bound by its chain of dependent loads - word, mask, query value - so the time moved by 1.4 % only;
+            // loading the next chunk's words and masks ahead of the replay was measured again with this loop: slower.)
+            const int trips = __reduce_max_sync(0xffffffffu, __popc(tm));
+            for (int k = 0; k < trips; k += 2) {
+                const bool a0 = tm != 0u; const int j0 = a0 ? __ffs(tm) - 1 : 0; tm &= tm - 1u;
+                const bool a1 = tm != 0u; const int j1 = a1 ? __ffs(tm) - 1 : 0; tm &= tm - 1u;
+                const int w0 = __shfl_sync(0xffffffffu, w, j0), w1 = __shfl_sync(0xffffffffu, w, j1);
+                const double d0 = __shfl_sync(0xffffffffu, dv, j0), d1 = __shfl_sync(0xffffffffu, dv, j1);
+                const double q0v = a0 ? __ldg(myq + w0) : 0.0, q1v = a1 ? __ldg(myq + w1) : 0.0;
+                if (a0) s += fabs(q0v - d0) - fabs(q0v) - fabs(d0);
+                if (a1) s += fabs(q1v - d1) - fabs(q1v) - fabs(d1);
             }
         }
         if (lane < nqt) {
