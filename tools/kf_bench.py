@@ -10,6 +10,13 @@ if os.environ.get("LIB"):
     frontend.LIB_PATH = os.path.join(ROOT, os.environ["LIB"])
 B, W, H = 128, 1241, 376
 frames = synth.stereo_batch(B, W, H, seed=0, unique=64)
+if os.environ.get("KFB_NOISE"):
+    # independent random textures (blurred noise, right = left shifted by a disparity): frames share few vocabulary words
+    rng = np.random.default_rng(7)
+    for i in range(B):
+        t = rng.integers(0, 256, (H // 4 + 2, W // 4 + 8), dtype=np.uint8).repeat(4, 0).repeat(4, 1).astype(np.float32)
+        t = (t + np.roll(t, 1, 0) + np.roll(t, 1, 1) + np.roll(t, 2, 0)) / 4
+        frames[i, 0] = t[:H, 16:16 + W].astype(np.uint8); frames[i, 1] = t[:H, 0:W].astype(np.uint8)
 fe = frontend.StereoFrontEnd(width=W, height=H, nlevels=8, nfeatures=1000, max_pairs=B)
 vz = np.load(os.path.join(ROOT, "tests", "golden", "voc_flat.npz"))
 voc = {k: (vz[k] if vz[k].ndim else vz[k].item()) for k in vz.files}
