@@ -230,7 +230,7 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
 #define FZ_KPW 8                         // keypoint slots a warp describes in turn (2: 0.424, 4: 0.404, 8: 0.400, 16: 0.412 ms)
 #endif
 #ifndef FZ_WARPS
-#define FZ_WARPS 5                       // 5 x 7.2 KB of patch buffers per CTA: six CTAs (30 warps) per SM (measured: 2 warps 0.411, 3: 0.408, 4: 0.400, 5: 0.392, 6: 0.400, 10: 0.417, 15: 0.424 ms)
+#define FZ_WARPS 5                       // 5 x 7.2 KB of patch buffers per CTA: five CTAs (25 warps) per SM - a sixth fits after trimming 1 KB and was measured slower (measured: 2 warps 0.411, 3: 0.408, 4: 0.400, 5: 0.392, 6: 0.400, 10: 0.417, 15: 0.424 ms)
 #endif
 #ifndef FZ_CTAS
 #define FZ_CTAS 6
