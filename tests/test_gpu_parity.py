@@ -428,6 +428,37 @@ def test_two_contexts_joined_streams(mods, scene_frames):
         a.close(); b.close()
 
 
+def test_dependent_launch_knob_changes_nothing(mods, scene_frames, monkeypatch):
+    """The kernels of a batch are launched programmatically dependent on each other (griddepcontrol.wait before the first access
+    to a predecessor's output); SFE_NO_PDL=1 falls back to plain stream order.  Graph replay, direct launches and the un-batched
+    call must give the same bytes either way, batch after batch."""
+    frontend, _ = mods
+    frames = scene_frames(3)
+    out = {}
+    for knob in ("pdl", "plain"):
+        if knob == "plain":
+            monkeypatch.setenv("SFE_NO_PDL", "1")            # read when the context is created
+        for graph in (1, 0):
+            fe = frontend.StereoFrontEnd(max_pairs=3, use_graph=graph)
+            try:
+                res = []
+                for it in range(3):
+                    fe.process_batch_host(frames if it != 1 else frames[::-1].copy())
+                    res.append([fe.get_values(p) for p in range(3)])
+                fe.process_stereo(frames[2, 0], frames[2, 1])
+                res.append([fe.get_values(0)])
+                out[(knob, graph)] = res
+            finally:
+                fe.close()
+    ref = out[("plain", 0)]
+    for key, res in out.items():
+        for a_batch, b_batch in zip(res, ref):
+            for a_pair, b_pair in zip(a_batch, b_batch):
+                assert len(a_pair[0]) > 100
+                for x, y in zip(a_pair, b_pair):
+                    assert np.array_equal(x, y), key
+
+
 @pytest.mark.parametrize("w,h,nlevels,scale,nfeat,fth,eth,bm,pm", [
     (401, 303, 1, 1.2, 150, 7, 31, 0, 0),         # single level, low FAST threshold (many quick-test survivors)
     (517, 389, 6, 1.1, 700, 35, 31, 0, 0),        # smaller scale step: wider source footprints in the pyramid kernel
