@@ -224,18 +224,17 @@ def main():
         fe.synchronize()
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------
-    # Two contexts (each with its own stream and resident batch) take the batches alternately: the tail of one batch's
-    # kernels overlaps the head of the next, and issue-bound kernels (FAST) co-run with the shared-memory-bound ones
-    # (describe) - measured +4-5 % over one context (tools/multi_ctx_probe.py).  One CUDA-event pair on the first
-    # context's stream spans everything: sfe_stream_wait joins the second stream before the stop event.
+    # One context replays its batch graph back to back.  (Round 1 alternated two contexts - overlapping tails gave +4-5 % then;
+    # with this round's kernels one, two and three contexts measure 108.5 k / 107.3 k / 108.4 k frames/s, tools/multi_ctx_probe.py,
+    # profiles/r02k_multi_ctx.json - so the simplest loop is also the fastest.)  One CUDA-event pair on the context's stream spans it.
     clocks = ClockSampler(local); clocks.start()        # spans warm-up, the resident loop and the end-to-end loop
     NCTX = 3
     extra = [frontend.StereoFrontEnd(width=W, height=H, nlevels=NLEVELS, nfeatures=NFEAT, max_pairs=B, device=local) for _ in range(NCTX - 1)]
-    rfe = (fe, extra[0])
+    rfe = (fe,)
     for f in rfe:
         f.upload(frames)
     for i_ in range(2 * args.warmup * BPS):
-        rfe[i_ % 2].process_device(B)
+        rfe[i_ % len(rfe)].process_device(B)
     for f in rfe:
         f.synchronize()
     kl, kr, dl, dr, m = fe.get_values(0)
@@ -244,10 +243,11 @@ def main():
     l0 = sum(f.kernel_launches() for f in rfe)
     fe.timer_start()
     for i_ in range(NB):
-        rfe[i_ % 2].process_device(B)
-    fe.stream_wait(rfe[1])
+        rfe[i_ % len(rfe)].process_device(B)
+    if len(rfe) > 1:
+        fe.stream_wait(rfe[1])
     ms = fe.timer_stop()
-    rfe[1].synchronize()
+    rfe[-1].synchronize()
     barrier()
     launches = sum(f.kernel_launches() for f in rfe) - l0
     ms = allmax(ms)
@@ -275,7 +275,7 @@ def main():
             oracle_cache[key] = (ol, odl, orr, odr, om)
         return oracle_cache[key]
     for p in par_pairs:
-        gl, gr, gdl, gdr, gm = rfe[(NB - 1) % 2].get_values(p) if NB > 1 else fe.get_values(p)
+        gl, gr, gdl, gdr, gm = rfe[(NB - 1) % len(rfe)].get_values(p)
         ol, odl, orr, odr, om = oracle_pair(p)
         same_kp = len(gl) == len(ol) and len(gr) == len(orr) and all(np.array_equal(gl[f], ol[f]) and np.array_equal(gr[f], orr[f])
                                                                    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"))
