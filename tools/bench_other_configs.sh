@@ -1,4 +1,5 @@
-python tools/variant_bench.py srba-stereo-slam_b200/libsrba_b200.so srba-stereo-slam_b200/variants/libsrba_b200_sel128.so srba-stereo-slam_b200/variants/libsrba_b200_sel512.so srba-stereo-slam_b200/variants/libsrba_b200_w10.so srba-stereo-slam_b200/variants/libsrba_b200_w15.so srba-stereo-slam_b200/variants/libsrba_b200_w5.so srba-stereo-slam_b200/variants/libsrba_b200_fast512.so srba-stereo-slam_b200/variants/libsrba_b200_sincos.so 2>&1 | grep -v VB_JSON | tee gpurun_out/vb9.log
-python tools/multi_ctx_probe.py > gpurun_out/multi_ctx_r02k.json 2>&1; cat gpurun_out/multi_ctx_r02k.json
-python bench.py --config a --steps 10 --warmup 3 > gpurun_out/bench_r02k_a.json 2> gpurun_out/bench_r02k_a.err; tail -c 300 gpurun_out/bench_r02k_a.json
-python bench.py --config e --steps 10 --warmup 3 > gpurun_out/bench_r02k_e.json 2> gpurun_out/bench_r02k_e.err; tail -c 300 gpurun_out/bench_r02k_e.json
+# usage: bash tools/bench_other_configs.sh TAG   -- one GPU call: the multi-context probe and the bench lines of configs[0] and configs[4]
+TAG=${1:-r02n}
+python tools/multi_ctx_probe.py > gpurun_out/${TAG}_multi_ctx.json 2>&1; cat gpurun_out/${TAG}_multi_ctx.json
+python bench.py --config a --steps 10 --warmup 3 > gpurun_out/bench_${TAG}_a.json 2> gpurun_out/bench_${TAG}_a.err; tail -c 300 gpurun_out/bench_${TAG}_a.json
+python bench.py --config e --steps 10 --warmup 3 > gpurun_out/bench_${TAG}_e.json 2> gpurun_out/bench_${TAG}_e.err; tail -c 300 gpurun_out/bench_${TAG}_e.json

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: retry_gpurun.sh <timeout_s> <command...>   -- retries while the pod answers "transient"
+# usage: tools/retry_gpurun.sh <timeout_s> <command...>   -- retries while the pod answers "transient"
 T=$1; shift
 for i in $(seq 1 60); do
   out=$(gpurun --timeout $T -- "$@" 2>&1)
