@@ -39,7 +39,7 @@ struct RowBandArgs {
     int max_dist, robust;
 };
 
-__global__ void __launch_bounds__(RB_THREADS)
+__global__ void __launch_bounds__(RB_THREADS, 8)     // 32 registers: the slice count below assumes 8 CTAs per SM (one wave); 39 registers cost a second wave, +16 us
 rowband_match_kernel(const RowBandArgs a)
 {
     extern __shared__ uint32_t dynm[];
