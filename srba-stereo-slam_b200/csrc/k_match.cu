@@ -25,10 +25,16 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
 // ------------------------------------------------------------------------------------------------
 // Row-band match.  Kernel 1: grid (slices, pairs) -- every CTA buckets the right keypoints of its pair by
 // image row in shared memory (counting sort, parallel scan) and matches its slice of the left keypoints,
-// one warp per left keypoint over the +-max_y_diff band.  Kernel 2: one CTA per pair, ordered compaction
+// one half-warp per left keypoint over the +-max_y_diff band.  Kernel 2: one CTA per pair, ordered compaction
 // (+ the mutual-best check) into the cv::DMatch list.
 // ------------------------------------------------------------------------------------------------
 #define RB_THREADS 256
+#ifndef RB_LANES
+#define RB_LANES 16               // lanes per left keypoint
+#endif
+#ifndef RB_WAVE
+#define RB_WAVE (148 * 8)
+#endif
 
 struct RowBandArgs {
     const sfe_keypoint* kps; const uint8_t* desc; const int32_t* kp_count;
@@ -98,24 +104,33 @@ rowband_match_kernel(const RowBandArgs a)
     // ---- one warp per left keypoint of this slice ------------------------------------------------
     uint32_t* best = a.best + (size_t)pair * a.kp_cap;
     uint32_t* owner = a.owner + (size_t)pair * a.kp_cap;
-    for (int i = i0 + warp; i < i1; i += RB_THREADS / 32) {
-        const float xl = kl[i].x, yl = kl[i].y;
-        const uint4 q0 = __ldg(dl + 2 * i), q1 = __ldg(dl + 2 * i + 1);
-        const int rlo = min(max((int)floorf(yl - a.max_y_diff), 0), H - 1);
-        const int rhi = min(max((int)floorf(yl + a.max_y_diff), 0), H - 1);
-        const int beg = row_start[rlo], end = row_start[rhi + 1];
+    // RB_LANES lanes per left keypoint: a +-2 row band holds ~13 candidates at 1000 keypoints, a half-warp is enough, and two
+    // independent keypoints per warp halve the number of trips through the chain of dependent loads (0.044 -> 0.038 ms; measured
+    // at 32 registers - at 39 the grid no longer fits one wave and every gain is lost)
+    constexpr int KPW = 32 / RB_LANES;                            // left keypoints a warp matches at once
+    const int half = lane / RB_LANES, hl = lane % RB_LANES;
+    for (int ib = i0 + KPW * warp; ib < i1; ib += KPW * (RB_THREADS / 32)) {     // warp-uniform trip count
+        const int i = ib + half;
+        const bool valid = i < i1;
         uint32_t key = 0xffffffffu;
-        for (int p = beg + lane; p < end; p += 32) {
-            const int j = sorted[p];
-            const float dy = fabsf(yl - kr[j].y), disp = xl - kr[j].x;
-            if (dy <= a.max_y_diff && disp >= a.min_disp && disp <= a.max_disp) {
-                const int d = hamming256(q0, q1, __ldg(dr + 2 * j), __ldg(dr + 2 * j + 1));
-                key = min(key, ((uint32_t)d << 16) | (uint32_t)j);
+        if (valid) {
+            const float xl = kl[i].x, yl = kl[i].y;
+            const uint4 q0 = __ldg(dl + 2 * i), q1 = __ldg(dl + 2 * i + 1);
+            const int rlo = min(max((int)floorf(yl - a.max_y_diff), 0), H - 1);
+            const int rhi = min(max((int)floorf(yl + a.max_y_diff), 0), H - 1);
+            const int beg = row_start[rlo], end = row_start[rhi + 1];
+            for (int p = beg + hl; p < end; p += RB_LANES) {
+                const int j = sorted[p];
+                const float dy = fabsf(yl - kr[j].y), disp = xl - kr[j].x;
+                if (dy <= a.max_y_diff && disp >= a.min_disp && disp <= a.max_disp) {
+                    const int d = hamming256(q0, q1, __ldg(dr + 2 * j), __ldg(dr + 2 * j + 1));
+                    key = min(key, ((uint32_t)d << 16) | (uint32_t)j);
+                }
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
-        if (lane == 0) {
+        for (int o = RB_LANES / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));     // stays inside the lane group
+        if (valid && hl == 0) {
             if (key != 0xffffffffu && (int)(key >> 16) > a.max_dist) key = 0xffffffffu;
             best[i] = key;
             if (a.robust && key != 0xffffffffu) atomicMin(&owner[key & 0xffffu], (key & 0xffff0000u) | (uint32_t)i);
@@ -186,7 +201,7 @@ void launch_match_rowband(sfe_context* c, int npairs)
     // As many slices as still make ONE wave of 8 CTAs per SM (the kernel is a latency chain per CTA: a second, partial wave
     // doubles its time), at least 64 left keypoints per slice.  128 pairs: 5 / 6 / 7 / 9 / 10 slices measured
     // 0.054 / 0.050 / 0.046 / 0.044 / 0.054 ms.
-    a.slices = std::max(1, std::min({ (148 * 8) / npairs, (c->cfg.nfeatures + 63) / 64, 32 }));
+    a.slices = std::max(1, std::min({ RB_WAVE / npairs, (c->cfg.nfeatures + 63) / 64, 32 }));
     if (a.robust) cudaMemsetAsync(c->d_rb_owner, 0xff, sizeof(uint32_t) * (size_t)npairs * a.kp_cap, c->stream);
     sfe_launch(c, !a.robust && (c->pdl_mask & 16), rowband_match_kernel, dim3(a.slices, npairs), dim3(RB_THREADS), rowband_smem(c), a);     // robust: a memset precedes it
     sfe_launch(c, (c->pdl_mask & 32) != 0, rowband_compact_kernel, dim3(npairs), dim3(RB_THREADS), 0, a);
