@@ -13,6 +13,7 @@
 // the 256 tests (one descriptor byte) with the pattern rotated in float, unfused, round-half-even through the
 // 1.5*2^23 magic add (bit-identical to cvRound of the CPU arithmetic); the biased integers index shared memory directly.
 #include "sfe_internal.cuh"
+#include <algorithm>
 
 __device__ const int8_t d_brief_pattern[256 * 4] = {
 #include "brief_pattern_31.inc"
@@ -230,10 +231,13 @@ describe_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__
 #define FZ_KPW 8                         // keypoint slots a warp describes in turn (2: 0.424, 4: 0.404, 8: 0.400, 16: 0.412 ms)
 #endif
 #ifndef FZ_WARPS
-#define FZ_WARPS 5                       // 5 x 7.2 KB of patch buffers per CTA: five CTAs (25 warps) per SM - a sixth fits after trimming 1 KB and was measured slower (measured: 2 warps 0.411, 3: 0.408, 4: 0.400, 5: 0.392, 6: 0.400, 10: 0.417, 15: 0.424 ms)
+#define FZ_WARPS 6                       // 6 x 7.2 KB of patch buffers per CTA, four resident CTAs (24 warps) per SM.  Static grid: 2 / 3 / 4 / 5 / 6 / 10 / 15 warps measured 0.411 / 0.408 / 0.400 / 0.392 / 0.400 / 0.417 / 0.424 ms; with the work counter 4 / 5 / 6 / 7 / 8 / 12 warps 0.404 / 0.390 / 0.384 / 0.406 / 0.390 / 0.394 ms
 #endif
 #ifndef FZ_CTAS
-#define FZ_CTAS 6
+#define FZ_CTAS 4
+#endif
+#ifndef FZ_RESIDENT
+#define FZ_RESIDENT 4                    // CTAs of FZ_WARPS warps that fit an SM (shared memory)
 #endif
 #define FZ_GROUPS 10                     // 4-column output groups covering x-18 .. x+18 for every alignment
 #define FZ_RB_PITCH (FZ_GROUPS * 4)      // row-sum words per row pair
@@ -243,13 +247,13 @@ __global__ void __launch_bounds__(FZ_WARPS * 32, FZ_CTAS)
 describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr,
                       const uint32_t* __restrict__ sel_xy, const float* __restrict__ sel_resp,
                       const int32_t* __restrict__ sel_count,
-                      sfe_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ kp_count)
+                      sfe_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int32_t* __restrict__ kp_count,
+                      int32_t* __restrict__ work_ctr, const int nimg)
 {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     __shared__ uint32_t pat_s[256];
     __shared__ uint32_t disc_mask[16 * 9];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int img = blockIdx.y;
     for (int t = tid; t < 256; t += FZ_WARPS * 32) pat_s[t] = reinterpret_cast<const uint32_t*>(d_brief_pattern)[8 * (t & 31) + (t >> 5)];
     for (int t = tid; t < 128; t += FZ_WARPS * 32) {
         const int av = t >> 3, k = t & 7, m = c_umax[av];
@@ -261,16 +265,26 @@ describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __rest
     pdl_wait();                                                                  // the selection lists are the previous kernel's output
     __syncthreads();
 
-    // slot -> (level, index): lanes 0..7 hold the per-level counts, an 8-lane scan gives the level boundaries (once per warp)
+    // Work items = (image, chunk of FZ_KPW keypoint slots), claimed by the warps from a global counter (the select kernel of the
+    // batch zeroed it): whichever warp is free takes the next item, so the grid - one resident wave - drains evenly instead of
+    // ending on a partial wave of 45-us CTAs.
+    const int chunks = (P.kp_cap + FZ_KPW - 1) / FZ_KPW;
+    const int nitems = nimg * chunks;
+    for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(work_ctr, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) break;
+    const int img = item / chunks, chunk = item - img * chunks;
+    // slot -> (level, index): lanes 0..7 hold the per-level counts, an 8-lane scan gives the level boundaries
     const int cnt = lane < P.nlevels ? sel_count[(size_t)img * P.nlevels + lane] : 0;
     int inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (blockIdx.x == 0 && tid == 7) kp_count[img] = inc;
-    // a warp describes FZ_KPW keypoint slots in turn: the per-CTA set-up (pattern table, disc masks) is paid once per 6 x FZ_KPW keypoints
+    for (int d = 1; d < 8; d <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t_; }
+    if (chunk == 0 && lane == 7) kp_count[img] = inc;
 #pragma unroll 1
     for (int kk = 0; kk < FZ_KPW; ++kk) {
-    const int slot = (blockIdx.x * FZ_KPW + kk) * FZ_WARPS + warp;
+    const int slot = chunk * FZ_KPW + kk;
     const uint32_t below = __ballot_sync(0xffffffffu, lane < P.nlevels && slot < inc);
     if (below == 0u) break;                                                      // warp-uniform; later slots are empty too
     const int level = __ffs(below) - 1;
@@ -424,6 +438,7 @@ describe_fused_kernel(const __grid_constant__ LevelPack P, const uint8_t* __rest
     }
     __syncwarp();                                                                // the next keypoint's staging overwrites the patch buffers
     }
+    }
 }
 
 bool describe_is_fused(const sfe_context* c)
@@ -440,9 +455,10 @@ static_assert(FZ_ROWS * FZ_PITCH >= BP_ROWS * BP_PITCH, "the blurred patch must 
 void launch_describe(sfe_context* c, int nimg)
 {
     if (describe_is_fused(c)) {
-        dim3 grid((c->pack.kp_cap + FZ_WARPS * FZ_KPW - 1) / (FZ_WARPS * FZ_KPW), nimg);
+        const int chunks = (c->pack.kp_cap + FZ_KPW - 1) / FZ_KPW;
+        dim3 grid(std::min((nimg * chunks + FZ_WARPS - 1) / FZ_WARPS, 148 * FZ_RESIDENT));     // one resident wave of persistent CTAs
         sfe_launch(c, (c->pdl_mask & 8) != 0, describe_fused_kernel, grid, dim3(FZ_WARPS * 32), FZ_WARPS * FZ_WARP_BYTES, c->pack, (const uint8_t*)c->d_pyr, (const uint32_t*)c->d_sel_xy,
-                   (const float*)c->d_sel_resp, (const int32_t*)c->d_sel_count, c->d_kp, c->d_desc, c->d_kp_count);
+                   (const float*)c->d_sel_resp, (const int32_t*)c->d_sel_count, c->d_kp, c->d_desc, c->d_kp_count, c->d_desc_ctr, nimg);
         return;
     }
     dim3 grid((c->pack.kp_cap + DESC_WARPS - 1) / DESC_WARPS, nimg);

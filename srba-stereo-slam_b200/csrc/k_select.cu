@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(SEL_THREADS, SEL_OCC)
 select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ pyr,
               const uint32_t* __restrict__ raw, const int32_t* __restrict__ raw_count,
               uint32_t* __restrict__ sel_xy, float* __restrict__ sel_resp, int32_t* __restrict__ sel_count,
-              int32_t* __restrict__ status, const int cand_cap)
+              int32_t* __restrict__ status, const int cand_cap, int32_t* __restrict__ next_ctr)
 {
     extern __shared__ uint32_t dyn[];
     uint32_t* cand_xy = dyn;                                    // [cand_cap]  (y<<16 | x)
@@ -87,6 +87,7 @@ select_kernel(const __grid_constant__ LevelPack P, const uint8_t* __restrict__ p
     for (int i = tid; i < SEL_SORT_CAP; i += SEL_THREADS) skey[i] = 0xffffffffu;     // padding of the rank-counting loop
     if (tid == 0) { s_n = 0; s_n2 = 0; }
     pdl_wait();
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) *next_ctr = 0;      // the describe kernel's work counter (it starts after this grid)
     int n = raw_count[(size_t)img * P.nlevels + level];
     if (n > g.raw_cap) { n = g.raw_cap; if (tid == 0) atomicOr(&status[img], SFE_ERR_CAPACITY); }
 
@@ -306,5 +307,5 @@ void launch_select(sfe_context* c, int nimg)
     const size_t smem = (size_t)cap * 8;
     dim3 grid(nimg, c->pack.nlevels);
     sfe_launch(c, (c->pdl_mask & 4) != 0, select_kernel, grid, dim3(SEL_THREADS), smem, c->pack, (const uint8_t*)c->d_pyr, (const uint32_t*)c->d_raw, (const int32_t*)c->d_raw_count,
-               c->d_sel_xy, c->d_sel_resp, c->d_sel_count, c->d_status, cap);
+               c->d_sel_xy, c->d_sel_resp, c->d_sel_count, c->d_status, cap, c->d_desc_ctr);
 }

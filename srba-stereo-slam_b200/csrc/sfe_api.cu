@@ -195,6 +195,8 @@ static int create_impl(sfe_context* c)
     }
     SFE_CUDA(c, dalloc(&c->d_raw, (size_t)NI * P.raw_img_stride));
     SFE_CUDA(c, dalloc(&c->d_raw_count, (size_t)NI * L));
+    SFE_CUDA(c, dalloc(&c->d_desc_ctr, (size_t)4));
+    SFE_CUDA(c, cudaMemset(c->d_desc_ctr, 0, 16));
     SFE_CUDA(c, dalloc(&c->d_sel_xy, (size_t)NI * P.sel_img_stride));
     SFE_CUDA(c, dalloc(&c->d_sel_resp, (size_t)NI * P.sel_img_stride));
     SFE_CUDA(c, dalloc(&c->d_sel_count, (size_t)NI * L));
@@ -346,7 +348,7 @@ extern "C" void sfe_destroy(sfe_context* c)
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto g : c->graphs) if (g) cudaGraphExecDestroy(g);
-    cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_raw); cudaFree(c->d_raw_count);
+    cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_raw); cudaFree(c->d_raw_count); cudaFree(c->d_desc_ctr);
     cudaFree(c->d_sel_xy); cudaFree(c->d_sel_resp); cudaFree(c->d_sel_count); cudaFree(c->d_kp); cudaFree(c->d_desc);
     cudaFree(c->d_rb_best); cudaFree(c->d_rb_owner); cudaFree(c->d_kp_count); cudaFree(c->d_matches); cudaFree(c->d_match_count); cudaFree(c->d_status);
     cudaFree(c->d_packed); cudaFree(c->d_ftile_tab); cudaFree(c->d_btile_tab); cudaFree(c->d_bf_q); cudaFree(c->d_bf_t); cudaFree(c->d_bf_best); cudaFree(c->d_bf_ofs);

@@ -152,6 +152,7 @@ struct sfe_context {
     sfe_keypoint* d_kp = nullptr;            // [NI][kp_cap]
     uint8_t* d_desc = nullptr;               // [NI][kp_cap][32]
     int32_t* d_kp_count = nullptr;           // [NI]
+    int32_t* d_desc_ctr = nullptr;           // work counter of the describe kernel (zeroed by the select kernel of the same batch)
     sfe_dmatch* d_matches = nullptr;         // [max_pairs][kp_cap]
     int32_t* d_match_count = nullptr;        // [max_pairs]
     uint32_t* d_rb_best = nullptr;           // [max_pairs][kp_cap] row-band match: packed best key per left keypoint
