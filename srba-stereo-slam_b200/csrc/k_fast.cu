@@ -243,10 +243,10 @@ fast_kernel(const __grid_constant__ LevelPack P, const int4* __restrict__ tile_t
     }
 }
 
-void launch_fast(sfe_context* c, int nimg)
+void launch_fast(sfe_context* c, int nimg, bool after_kernel)
 {
     const int ntiles = c->pack.ftile_prefix[c->pack.nlevels];
     if (ntiles == 0) return;
     dim3 grid(ntiles, nimg);
-    sfe_launch(c, c->pack.nlevels > 1 && (c->pdl_mask & 2), fast_kernel, grid, dim3(256), 0, c->pack, (const int4*)c->d_ftile_tab, c->d_raw, c->d_raw_count, c->fast_th);
+    sfe_launch(c, after_kernel && c->pack.nlevels > 1 && (c->pdl_mask & 2), fast_kernel, grid, dim3(256), 0, c->pack, (const int4*)c->d_ftile_tab, c->d_raw, c->d_raw_count, c->fast_th);
 }

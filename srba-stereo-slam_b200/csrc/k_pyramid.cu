@@ -22,7 +22,7 @@
 
 struct PyrArgs {
     uint8_t* dst; int dpitch; size_t dimg_bytes;
-    int dw, dh;
+    int dw, dh, img0;           // first image of this launch (the batch may be split over two streams)
     const uint32_t* gtab;       // per group of 4 destination columns: {src base, byte selectors, 4 x (a0 | a1<<16)}, 6 words
     const int4* ytab;           // per destination row: {src row 0, src row 1 (both clamped to the image) as byte offsets into the
                                 // horizontal-pass buffer (row * PYR_HPW * 4), b0 << 16, b1 << 16}
@@ -45,7 +45,7 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     __shared__ alignas(16) uint32_t hbuf[PYR_BOX_H * PYR_HPW];          // horizontal pass (>> 4 in the 2.4 arithmetic), two u16 per word
     __shared__ alignas(16) int4 yts[PYR_TH];                            // the tile's rows of the vertical table
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * PYR_TW, y0 = blockIdx.y * PYR_TH, img = blockIdx.z;
+    const int x0 = blockIdx.x * PYR_TW, y0 = blockIdx.y * PYR_TH, img = a.img0 + blockIdx.z;
     const int bx0 = a.tile_bx[blockIdx.x];        // TMA: box start must be 16-byte aligned in x
     const int sy0 = a.tile_sy[blockIdx.y];        // first source row of the tile
     if (tid == 0) {
@@ -115,12 +115,12 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, const PyrArgs a)
     }
 }
 
-void launch_pyramid_level(sfe_context* c, int level, int nimg)
+void launch_pyramid_level(sfe_context* c, int level, int img0, int nimg)
 {
     const LevelGeom& g = c->pack.g[level];
     PyrArgs a;
     a.dst = c->d_pyr + g.lvl_ofs; a.dpitch = g.pitch; a.dimg_bytes = g.img_bytes;
-    a.dw = g.w; a.dh = g.h;
+    a.dw = g.w; a.dh = g.h; a.img0 = img0;
     a.gtab = c->d_gtab[level]; a.ytab = c->d_ytab[level];
     const int ntx = (g.w + PYR_TW - 1) / PYR_TW, nty = (g.h + PYR_TH - 1) / PYR_TH;
     const int sh = c->pack.g[level - 1].h;

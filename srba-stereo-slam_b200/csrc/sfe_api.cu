@@ -125,6 +125,11 @@ static int create_impl(sfe_context* c)
     SFE_CUDA(c, cudaGetDeviceProperties(&prop, f.device));
     if (prop.major != 10) { c->err = std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library is built for sm_100a only"; return SFE_ERR_CUDA; }
     SFE_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SFE_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int b = 0; b < 3; ++b) {
+        SFE_CUDA(c, cudaStreamCreateWithFlags(&c->stream2[b], cudaStreamNonBlocking));
+        SFE_CUDA(c, cudaEventCreateWithFlags(&c->ev_branch[b], cudaEventDisableTiming));
+    }
     SFE_CUDA(c, cudaEventCreate(&c->ev_start));
     SFE_CUDA(c, cudaEventCreate(&c->ev_stop));
     for (int i = 0; i <= ST_COUNT; ++i) SFE_CUDA(c, cudaEventCreate(&c->ev_stage[i]));
@@ -188,6 +193,8 @@ static int create_impl(sfe_context* c)
     SFE_CUDA(c, cudaMemset(c->d_pyr, 0, arena));
     c->force_unfused = getenv("SFE_FORCE_UNFUSED_BLUR") != nullptr;
     c->pdl = getenv("SFE_NO_PDL") == nullptr;
+    c->pyr_fork = getenv("SFE_NO_PYR_FORK") == nullptr;
+    if (getenv("SFE_PYR_BRANCHES")) c->pyr_branches = std::min(4, std::max(2, atoi(getenv("SFE_PYR_BRANCHES"))));
     if (getenv("SFE_PDL_MASK")) c->pdl_mask = atoi(getenv("SFE_PDL_MASK"));
     if (!describe_is_fused(c)) {           // the blurred arena only exists where a separate blur kernel runs (float mode, edge_threshold < 22)
         SFE_CUDA(c, dalloc(&c->d_blur, arena));
@@ -359,6 +366,8 @@ extern "C" void sfe_destroy(sfe_context* c)
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
     for (int i = 0; i <= ST_COUNT; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int b = 0; b < 3; ++b) { if (c->ev_branch[b]) cudaEventDestroy(c->ev_branch[b]); if (c->stream2[b]) cudaStreamDestroy(c->stream2[b]); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -396,9 +405,27 @@ static void enqueue_kernels(sfe_context* c, int npairs)
     const int nimg = 2 * npairs, L = c->pack.nlevels;
     cudaMemsetAsync(c->d_raw_count, 0, sizeof(int32_t) * (size_t)nimg * L, c->stream);
     stage_mark(c, ST_PYRAMID);
-    for (int l = 1; l < L; ++l) launch_pyramid_level(c, l, nimg);
+    // The pyramid is a chain of L-1 dependent launches whose grids shrink level by level; every launch ends on a partial wave
+    // (2.08 waves at level 7: a third round for 8 % of the CTAs).  With the batch split in two image halves on two streams
+    // (forked and joined with events, also inside the captured graph) one half's tail runs under the other half's next level.
+    const bool fork = L > 2 && nimg >= 64 && !c->profiling && c->pyr_fork;
+    if (fork) {
+        const int NBR = c->pyr_branches;                          // 2 .. 4 image ranges, the first on the main stream
+        cudaEventRecord(c->ev_fork, c->stream);
+        for (int b = 1; b < NBR; ++b) cudaStreamWaitEvent(c->stream2[b - 1], c->ev_fork, 0);
+        for (int l = 1; l < L; ++l)
+            for (int b = 0; b < NBR; ++b) {
+                const int i0 = (int)((long long)nimg * b / NBR), i1 = (int)((long long)nimg * (b + 1) / NBR);
+                c->launch_stream = b ? c->stream2[b - 1] : nullptr;
+                launch_pyramid_level(c, l, i0, i1 - i0);
+            }
+        c->launch_stream = nullptr;
+        for (int b = 1; b < NBR; ++b) { cudaEventRecord(c->ev_branch[b - 1], c->stream2[b - 1]); cudaStreamWaitEvent(c->stream, c->ev_branch[b - 1], 0); }
+    } else {
+        for (int l = 1; l < L; ++l) launch_pyramid_level(c, l, 0, nimg);
+    }
     stage_mark(c, ST_FAST);
-    launch_fast(c, nimg);
+    launch_fast(c, nimg, !fork);
     stage_mark(c, ST_SELECT);
     launch_select(c, nimg);
     stage_mark(c, ST_BLUR);

@@ -127,6 +127,9 @@ struct sfe_context {
     sfe_config cfg;
     int fast_th, orb_th;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2[3] = {};            // further branches of the pyramid phase (forked from / joined into `stream`, also inside the batch graph)
+    cudaStream_t launch_stream = nullptr;    // where sfe_launch puts the next kernel (nullptr: `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_branch[3] = {};
     std::string err;
     LevelPack pack;                          // host copy (passed by value at launch)
     std::vector<std::vector<int2>> xtab, ytab;   // host resize tables: {src offset, a0 | a1<<16} per destination column / row
@@ -137,6 +140,8 @@ struct sfe_context {
     CUtensorMap pyrsrc_map[SFE_MAX_LEVELS];  // 176x48-box maps over the same levels, source side of the pyramid kernel
     int NI = 0;                              // images the arenas are sized for (2*max_pairs)
     int pdl_mask = 0x3f;                     // debugging: which kernels of the chain may launch dependently (SFE_PDL_MASK)
+    int pyr_branches = 2;                    // image ranges of the forked pyramid phase (SFE_PYR_BRANCHES=2..4)
+    bool pyr_fork = true;                    // pyramid phase on two streams (SFE_NO_PYR_FORK=1: one stream; A-B timing)
     bool pdl = true;                         // programmatic dependent launch between the kernels of a batch (SFE_NO_PDL=1 turns it off: A-B timing)
     bool force_unfused = false;              // debugging / A-B timing: keep the separate blur kernel even where the fused describe applies
     int sel_cand_cap = 0;                    // select kernel: shared candidate list capacity
@@ -210,7 +215,7 @@ template <typename... KArgs, typename... Args>
 inline void sfe_launch(sfe_context* c, bool dependent, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->launch_stream ? c->launch_stream : c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (dependent && c->pdl) ? 1 : 0;
@@ -222,8 +227,8 @@ inline void sfe_launch(sfe_context* c, bool dependent, void (*kern)(KArgs...), d
 void sfe_raise_dynamic_smem(const void* func, int device, int bytes);
 
 // kernel launchers (defined in the per-stage .cu files)
-void launch_pyramid_level(sfe_context* c, int level, int nimg);
-void launch_fast(sfe_context* c, int nimg);
+void launch_pyramid_level(sfe_context* c, int level, int img0, int nimg);      // images [img0, img0 + nimg)
+void launch_fast(sfe_context* c, int nimg, bool after_kernel);   // after_kernel: the previous node of the stream is one kernel (may launch dependently)
 void launch_select(sfe_context* c, int nimg);
 void prepare_select(sfe_context* c);
 void prepare_rowband(sfe_context* c);
