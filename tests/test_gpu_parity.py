@@ -459,6 +459,36 @@ def test_dependent_launch_knob_changes_nothing(mods, scene_frames, monkeypatch):
                     assert np.array_equal(x, y), key
 
 
+def test_forked_pyramid_graph_equals_direct_launches(mods, scene_frames, monkeypatch):
+    """From 64 images on, the batch graph runs the pyramid phase as two image halves on two streams (fork / join events captured
+    into the graph).  The graph replay must give, pair for pair, what plain direct launches on one stream give, with and without
+    the fork (SFE_NO_PYR_FORK=1), batch after batch."""
+    frontend, _ = mods
+    B = 40                                                            # 80 images: above the fork threshold, halves of 40
+    base = scene_frames(4)
+    frames = np.ascontiguousarray(np.concatenate([base] * (B // 4), axis=0))
+    frames[1::2] = frames[1::2, :, ::-1].copy()[:, ::-1]              # every other pair swapped L/R: the halves differ
+    ref = frontend.StereoFrontEnd(max_pairs=B, use_graph=0)
+    try:
+        ref.process_batch_host(frames)
+        want = [ref.get_values(p) for p in range(B)]
+    finally:
+        ref.close()
+    assert len(want[0][0]) > 100
+    for knob in ("fork", "one stream"):
+        if knob == "one stream":
+            monkeypatch.setenv("SFE_NO_PYR_FORK", "1")
+        fe = frontend.StereoFrontEnd(max_pairs=B, use_graph=1)
+        try:
+            for it in range(3):
+                fe.process_batch_host(frames)
+                for p in range(B):
+                    for x, y in zip(fe.get_values(p), want[p]):
+                        assert np.array_equal(x, y), (knob, it, p)
+        finally:
+            fe.close()
+
+
 @pytest.mark.parametrize("w,h,nlevels,scale,nfeat,fth,eth,bm,pm", [
     (401, 303, 1, 1.2, 150, 7, 31, 0, 0),         # single level, low FAST threshold (many quick-test survivors)
     (517, 389, 6, 1.1, 700, 35, 31, 0, 0),        # smaller scale step: wider source footprints in the pyramid kernel
