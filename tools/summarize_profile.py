@@ -41,7 +41,12 @@ def main():
     for r in rows:
         k = short(r[ix["Kernel Name"]]); grid = r[ix["Grid Size"]]
         dims = [d.strip() for d in grid.strip("()").split(",")]
-        full = (("256" in dims) or (k.startswith("rowband") and "128" in dims)) and k != "unpack_kernel"   # image / pair axis of a full batch
+        # launches of a full 128-pair batch: image axis 256 (or 128: the pyramid phase runs as two image halves), pair axis 128,
+        # the describe kernel's persistent grid (one resident wave; the single-pair launches have ~60 CTAs)
+        if k == "pyramid_kernel": full = dims[-1] in ("128", "256")
+        elif k.startswith("describe"): full = ("256" in dims) or int(dims[0]) >= 400
+        elif k.startswith("rowband"): full = "128" in dims
+        else: full = ("256" in dims) and k != "unpack_kernel"
         if k == "fast_kernel" and full:
             nbatch += 1
         if full and k in STAGE:
